@@ -1,0 +1,219 @@
+/*
+ * phantomsdr_b200.h - C ABI of the B200-native spectrum / channeliser engine.
+ *
+ * This is the drop-in boundary for ONE hot path of PhantomSDR: the FFT backend behind
+ * src/fft.h:33-63 (class FFT) and the two slot callbacks it feeds,
+ * AudioClient::send_audio (src/signal.h:67, src/signal.cpp:102-298) and
+ * WaterfallClient::send_waterfall (src/waterfall.h:13, src/waterfall.cpp:44-51).
+ * Citations are relative to the reference tree. INTEGRATION.md shows the C++ adapter a
+ * maintainer would add (class B200FFT : public FFT -> these calls).
+ *
+ * Conventions (mirroring the reference, src/fft.h:39-48): every call returns int, 0 = OK,
+ * negative = -errno style failure (B200_E*). No C++ types, no torch types, no exceptions cross
+ * this boundary. All entry points of one engine are single-caller (the reference calls them
+ * from its one fft_thread, src/spectrumserver.cpp:245). There is NO CPU fallback: if no CUDA
+ * device is usable, b200_engine_create fails with B200_ENODEV (the reference's cuFFT ctor
+ * throws "No CUDA devices found", src/fft_cuda.cu:10-13).
+ */
+#ifndef PHANTOMSDR_B200_H
+#define PHANTOMSDR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+/* error codes (negative errno values) */
+#define B200_OK 0
+#define B200_EINVAL (-22)
+#define B200_ENOMEM (-12)
+#define B200_ENODEV (-19)
+#define B200_ENOTSUP (-95)
+#define B200_ESTATE (-1)  /* call out of order (e.g. execute before plan) */
+#define B200_ECUDA (-5)   /* a CUDA runtime call failed; see b200_last_error() */
+
+/* FFT::direction, src/fft.h:35 */
+#define B200_FORWARD 0
+#define B200_BACKWARD 1
+
+/* enum demodulation_mode { USB, LSB, AM, FM }, src/client.h:43 */
+#define B200_USB 0
+#define B200_LSB 1
+#define B200_AM 2
+#define B200_FM 3
+
+/* raw sample formats of SampleConverter<T>, src/samplereader.cpp:29-66 */
+#define B200_FMT_F32 0
+#define B200_FMT_U8 1
+#define B200_FMT_S8 2
+#define B200_FMT_U16 3
+#define B200_FMT_S16 4
+
+typedef struct b200_engine b200_engine;
+
+int b200_abi_version(void);
+/* Human-readable text of the last failure on this thread (never NULL). */
+const char *b200_last_error(void);
+/* Number of usable CUDA devices (0 if none / driver missing). */
+int b200_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * FFT backend group  - replaces class FFTW / class cuFFT (src/fft.h:93-145)
+ * ------------------------------------------------------------------------------------------ */
+
+/* FFT::FFT(size, nthreads, downsample_levels, brightness_offset), src/fft.h:36, src/fft_impl.cpp:63-70.
+ * Builds the periodic Hann window on the host exactly as build_hann_window (src/utils/dsp.cpp:6-11)
+ * and uploads it; size_log2 = round(log2(size)) + brightness_offset. `size` must be a power of
+ * two (2^16..2^20 for c2c, 2^17..2^21 for r2c in this version -> B200_ENOTSUP otherwise).
+ * `nthreads` is accepted and ignored. `device` is the CUDA ordinal. */
+int b200_engine_create(b200_engine **out, size_t size, int nthreads, int downsample_levels, int brightness_offset,
+                       int device);
+void b200_engine_destroy(b200_engine *e);
+
+/* FFT::set_output_additional_size, src/fft.h:41, called before planning (src/spectrumserver.cpp:214). */
+int b200_set_output_additional_size(b200_engine *e, size_t n);
+
+/* FFT::malloc / FFT::free, src/fft.h:37-38: the caller's 3-deep input ring (src/fft.cpp:17-22).
+ * Returns page-locked host memory (as cuFFT::malloc does, src/fft_cuda.cu:22-28); NULL on failure. */
+float *b200_malloc(b200_engine *e, size_t nfloats);
+void b200_free(b200_engine *e, float *buf);
+
+/* FFT::plan_c2c / plan_r2c, src/fft.h:39-40; called once (src/fft.cpp:25-29). `options` (FFTW flags)
+ * is ignored; direction must be B200_FORWARD (the only one the path uses, src/fft.cpp:28). */
+int b200_plan_c2c(b200_engine *e, int direction, int options);
+int b200_plan_r2c(b200_engine *e, int options);
+
+/* FFT::get_output_buffer / get_quantized_buffer, src/fft.h:43-45. Stable, CPU-dereferenceable
+ * (page-locked host mirrors refreshed by b200_execute). Output: complex float32 interleaved,
+ * normalised by 1/size, natural FFT order; c2c: size + additional_size bins (the caller performs
+ * the wrap memcpy itself, src/fft.cpp:96-97; the engine also fills the tail so device-side
+ * clients see it); r2c: size/2 + 1 bins. Quantized: int8 pyramid, level i at offset
+ * sum_{j<i}(R >> j), display order (src/fft_impl.cpp:146-173, src/websocket.cpp:207-236). */
+float *b200_get_output_buffer(b200_engine *e);
+int8_t *b200_get_quantized_buffer(b200_engine *e);
+
+/* FFT::load_real_input / load_complex_input, src/fft.h:46-47: a1 = older half, a2 = newer half
+ * (src/fft.cpp:51-71). Host pointers, preferably from b200_malloc. Asynchronous: enqueues the
+ * host->device copy of the halves; the window multiply is fused into the FFT's first pass. If a1
+ * is the pointer passed as a2 by the previous call, it is assumed unchanged and NOT re-uploaded
+ * (the reference ring guarantees this); b200_set_option(B200_OPT_RELOAD_BOTH, 1) disables that. */
+int b200_load_real_input(b200_engine *e, const float *a1, const float *a2);
+int b200_load_complex_input(b200_engine *e, const float *a1, const float *a2);
+
+/* FFT::execute, src/fft.h:48, src/fft_impl.cpp:144-174. Synchronous: on return the host mirrors
+ * selected by B200_OPT_HOST_MIRROR hold the spectrum and the pyramid of the loaded frame. */
+int b200_execute(b200_engine *e);
+
+#define B200_OPT_RELOAD_BOTH 1   /* 0 (default) / 1 */
+#define B200_OPT_HOST_MIRROR 2   /* bitmask: 1 = spectrum, 2 = pyramid; default 3 */
+#define B200_OPT_INPUT_FORMAT 3  /* B200_FMT_*: format of the halves given to b200_load_raw_input */
+int b200_set_option(b200_engine *e, int option, int value);
+
+/* SURVEY 8f N1 - SampleConverter<T>::read fused into the first FFT pass: halves are raw
+ * u8/s8/u16/s16 samples (format from B200_OPT_INPUT_FORMAT), converted on the GPU exactly as
+ * src/samplereader.cpp:29-40,59-66 ((x ^ topbit) as signed / 2^(bits-1)). */
+int b200_load_raw_input(b200_engine *e, const void *a1, const void *a2);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-resident streaming form of the same path (inputs already in HBM).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Device buffers owned by the engine (valid after planning). */
+void *b200_device_spectrum(b200_engine *e);  /* float2[R + additional] (c2c) / float2[size/2 + 1] (r2c) */
+void *b200_device_quantized(b200_engine *e); /* int8 pyramid */
+void *b200_device_hop_ring(b200_engine *e);  /* hop ring: nhops x hop_floats float32 */
+size_t b200_hop_floats(b200_engine *e);      /* floats per hop: size (c2c) or size/2 (r2c) */
+size_t b200_spectrum_bins(b200_engine *e);   /* bins incl. tail */
+size_t b200_pyramid_bytes(b200_engine *e);
+/* (Re)allocate the device hop ring with `nhops` hops (>= 2; default 3). */
+int b200_set_hop_ring(b200_engine *e, size_t nhops);
+/* Forward FFT + pyramid of the frame made of hops (hop_index, hop_index+1) mod nhops of the device
+ * ring. Asynchronous on the engine's stream; no host copies. Same kernels as b200_execute. */
+int b200_execute_device(b200_engine *e, size_t hop_index);
+/* Streaming batch: `nframes` consecutive 50%-overlapped frames (frame f = hops hop_index+f,
+ * hop_index+f+1) in one launch per kernel. b200_set_batch_frames(F) sizes the device outputs for
+ * F frames (default 1): frame f's spectrum is at b200_device_spectrum() + f*b200_spectrum_stride()
+ * float2, its pyramid at b200_device_quantized() + f*b200_pyramid_stride() bytes. */
+int b200_set_batch_frames(b200_engine *e, int max_frames);
+int b200_execute_device_batch(b200_engine *e, size_t hop_index, int nframes);
+size_t b200_spectrum_stride(b200_engine *e);
+size_t b200_pyramid_stride(b200_engine *e);
+/* Wait for everything enqueued on the engine's stream. */
+int b200_sync(b200_engine *e);
+/* The engine's cudaStream_t (as void*), so callers can order their own work / events on it. */
+void *b200_stream(b200_engine *e);
+/* Adopt `dev_ptr` (device memory of b200_spectrum_bins() float2) as the spectrum buffer the client
+ * kernels read - used on non-ingest ranks, where the frame arrives by NCCL broadcast / peer store.
+ * Pass NULL to go back to the engine-owned buffer. */
+int b200_bind_spectrum(b200_engine *e, void *dev_ptr);
+/* Ingest rank only: additionally store every spectrum frame into these peer buffers (device
+ * pointers valid on this device, e.g. from b200_ipc_open) from inside the last FFT pass, so the
+ * NVLink transfer overlaps the butterflies. npeers = 0 turns it off. */
+int b200_set_peer_spectra(b200_engine *e, int npeers, void *const *dev_ptrs);
+/* CUDA IPC helpers for the above (64-byte handles). */
+int b200_ipc_export(b200_engine *e, const void *dev_ptr, uint8_t handle[64]);
+int b200_ipc_open(b200_engine *e, const uint8_t handle[64], void **dev_ptr);
+int b200_ipc_close(b200_engine *e, void *dev_ptr);
+
+/* ------------------------------------------------------------------------------------------
+ * Signal slot group - replaces N x AudioClient::send_audio (src/signal.cpp:102-298) and the
+ * slice index math of broadcast_server::signal_loop (src/websocket.cpp:156-185).
+ * ------------------------------------------------------------------------------------------ */
+
+/* AudioClient::AudioClient scratch/state for up to max_clients slots (src/signal.cpp:7-79):
+ * audio_fft_size (multiple of 4, src/spectrumserver.cpp:151), DCBlocker(audio_max_sps/750*2),
+ * AGC(0.2, 50 ms, 300 ms, 200 ms, audio_max_sps). */
+int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int audio_max_sps);
+/* New connection in `slot` (src/websocket.cpp:129-150): zeroed state, range and mode set. */
+int b200_client_open(b200_engine *e, int slot, int l, double audio_mid, int r, int demodulation);
+/* AudioClient::on_window_message, src/signal.cpp:300-314: validates 0 <= l <= r < R, r - l <= n;
+ * returns B200_EINVAL (state untouched) when the reference would silently ignore the message. */
+int b200_client_set_window(b200_engine *e, int slot, int l, double audio_mid, int r);
+/* AudioClient::on_demodulation_message, src/signal.cpp:316-328: sets the mode and resets the AGC. */
+int b200_client_set_demodulation(b200_engine *e, int slot, int demodulation);
+/* AudioClient::on_close, src/signal.cpp:330-336. */
+int b200_client_close(b200_engine *e, int slot);
+
+/* One signal_loop() pass: every open client, visited in the reference's (l, r)-sorted multimap
+ * order, demodulates frame `frame_num` (the server-global counter, src/websocket.cpp:182) from the
+ * current spectrum. Host outputs (page-locked preferred), indexed by slot:
+ *   pcm_out  [max_clients][audio_fft_size/2] int32  - what encoder->process receives (signal.cpp:291)
+ *   pwr_out  [max_clients] float                   - average_power of set_data (signal.cpp:287)
+ *   valid_out[max_clients] uint8                   - 0 where the reference drops the frame (NaN guard,
+ *                                                    signal.cpp:266-271) or the slot is closed
+ * Any of them may be NULL. Synchronous. */
+int b200_clients_execute(b200_engine *e, uint64_t frame_num, int32_t *pcm_out, float *pwr_out, uint8_t *valid_out);
+/* Asynchronous device-only form (results stay in device memory; see b200_device_pcm). With
+ * nframes > 1 the clients run frames frame_num .. frame_num+nframes-1 of the last
+ * b200_execute_device_batch in order, carrying their state from frame to frame. */
+int b200_clients_execute_device(b200_engine *e, uint64_t frame_num, int nframes);
+void *b200_device_pcm(b200_engine *e);   /* int32 [frames][max_clients][n/2] */
+void *b200_device_pwr(b200_engine *e);   /* float [frames][max_clients] */
+void *b200_device_valid(b200_engine *e); /* uint8 [frames][max_clients] */
+/* Copy the results of the last b200_clients_execute_device (frame index `frame` of the batch) to
+ * host buffers laid out as in b200_clients_execute. Synchronous. */
+int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_out, uint8_t *valid_out);
+/* Test tap: audio_real[0..n/2) before DC removal (signal.cpp:274) of the last executed frame,
+ * copied to host float [max_clients][n/2]. */
+int b200_clients_read_pre_dc(b200_engine *e, float *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Waterfall slot group - replaces N x WaterfallClient::send_waterfall (src/waterfall.cpp:44-51)
+ * and the level-offset math of waterfall_loop (src/websocket.cpp:207-236).
+ * ------------------------------------------------------------------------------------------ */
+/* Gathers, for client i, quantized[level_offset(level[i]) + l[i] .. + r[i]) into out + out_offsets[i]
+ * (host). Synchronous. The labels the reference sends are l << level, r << level (waterfall.cpp:47). */
+int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const int *l, const int *r,
+                          const size_t *out_offsets, int8_t *out);
+
+/* Kernel-launch counter since creation (for bench.py's gpu_launches). */
+uint64_t b200_launch_count(b200_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHANTOMSDR_B200_H */

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's FFT-backend interface and client slots, over the C ABI.
+
+``B200FFT`` has the method names, argument meaning and call order of ``class FFT``
+(reference src/fft.h:33-63): ``malloc/free``, ``set_output_additional_size``,
+``plan_c2c/plan_r2c``, ``load_real_input/load_complex_input``, ``execute``,
+``get_output_buffer/get_quantized_buffer``. The audio clients that the reference runs one
+``AudioClient::send_audio`` task at a time (src/signal.cpp:102-298, src/websocket.cpp:156-185) are
+a batched slot table here (``clients_*``). Every method is a thin call into
+``libphantomsdr_b200.so``; nothing is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import B200Error, check  # noqa: F401
+
+FORWARD, BACKWARD = 0, 1
+FMT_F32, FMT_U8, FMT_S8, FMT_U16, FMT_S16 = 0, 1, 2, 3, 4
+OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT = 1, 2, 3
+_FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
+
+
+def device_count() -> int:
+    return _ffi.lib().b200_device_count()
+
+
+def _host_view(ptr: int, count: int, dtype) -> np.ndarray:
+    nbytes = count * np.dtype(dtype).itemsize
+    buf = (C.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class _DevArray:
+    """Zero-copy handle on engine-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def _ptr(a) -> int:
+    if a is None:
+        return 0
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+class B200FFT:
+    """FFT backend on one B200. Mirrors ``class FFT`` / ``class cuFFT`` (src/fft.h:33-63,127-145)."""
+
+    def __init__(self, size: int, nthreads: int = 1, downsample_levels: int = 1, brightness_offset: int = 0,
+                 device: int = 0):
+        self.L = _ffi.lib()
+        self.size = int(size)
+        self.levels = int(downsample_levels)
+        self.device = device
+        self.additional = 0
+        self.is_real: Optional[bool] = None
+        self._bufs = {}
+        h = C.c_void_p()
+        check(self.L.b200_engine_create(C.byref(h), self.size, nthreads, downsample_levels, brightness_offset, device))
+        self.h = h
+        self.n_audio = 0
+        self.max_clients = 0
+
+    # ---- class FFT surface -------------------------------------------------------------------
+    def set_output_additional_size(self, n: int) -> None:
+        check(self.L.b200_set_output_additional_size(self.h, n))
+        self.additional = int(n)
+
+    def malloc(self, nfloats: int) -> np.ndarray:
+        p = self.L.b200_malloc(self.h, nfloats)
+        if not p:
+            raise B200Error(-12, self.L.b200_last_error().decode())
+        a = _host_view(p, nfloats, np.float32)
+        self._bufs[a.ctypes.data] = p
+        return a
+
+    def free(self, buf: np.ndarray) -> None:
+        p = self._bufs.pop(buf.ctypes.data, None)
+        if p:
+            self.L.b200_free(self.h, p)
+
+    def plan_c2c(self, direction: int = FORWARD, options: int = 0) -> int:
+        check(self.L.b200_plan_c2c(self.h, direction, options))
+        self.is_real = False
+        return 0
+
+    def plan_r2c(self, options: int = 0) -> int:
+        check(self.L.b200_plan_r2c(self.h, options))
+        self.is_real = True
+        return 0
+
+    @property
+    def result_size(self) -> int:
+        return self.size // 2 if self.is_real else self.size
+
+    def get_output_buffer(self) -> np.ndarray:
+        """float32 view of outbuf (complex interleaved), stable for the engine's lifetime."""
+        n = self.size + 2 if self.is_real else 2 * (self.size + self.additional)
+        return _host_view(self.L.b200_get_output_buffer(self.h), n, np.float32)
+
+    def get_quantized_buffer(self) -> np.ndarray:
+        return _host_view(self.L.b200_get_quantized_buffer(self.h), self.L.b200_pyramid_bytes(self.h), np.int8)
+
+    def load_real_input(self, a1: np.ndarray, a2: np.ndarray) -> int:
+        check(self.L.b200_load_real_input(self.h, _ptr(a1), _ptr(a2)))
+        return 0
+
+    def load_complex_input(self, a1: np.ndarray, a2: np.ndarray) -> int:
+        check(self.L.b200_load_complex_input(self.h, _ptr(a1), _ptr(a2)))
+        return 0
+
+    def load_raw_input(self, a1: np.ndarray, a2: np.ndarray) -> int:
+        """SampleConverter<T> fused on the GPU (src/samplereader.cpp:29-66); dtype picks the format."""
+        check(self.L.b200_set_option(self.h, OPT_INPUT_FORMAT, _FMT_OF_DTYPE[a1.dtype.name]))
+        check(self.L.b200_load_raw_input(self.h, _ptr(a1), _ptr(a2)))
+        return 0
+
+    def execute(self) -> int:
+        check(self.L.b200_execute(self.h))
+        return 0
+
+    def set_option(self, option: int, value: int) -> None:
+        check(self.L.b200_set_option(self.h, option, value))
+
+    # ---- device-resident streaming form ------------------------------------------------------
+    def set_hop_ring(self, nhops: int) -> None:
+        check(self.L.b200_set_hop_ring(self.h, nhops))
+        self.nhops = nhops
+
+    def set_batch_frames(self, frames: int) -> None:
+        check(self.L.b200_set_batch_frames(self.h, frames))
+
+    @property
+    def hop_floats(self) -> int:
+        return self.L.b200_hop_floats(self.h)
+
+    @property
+    def spectrum_bins(self) -> int:
+        return self.L.b200_spectrum_bins(self.h)
+
+    @property
+    def spectrum_stride(self) -> int:
+        return self.L.b200_spectrum_stride(self.h)
+
+    @property
+    def pyramid_bytes(self) -> int:
+        return self.L.b200_pyramid_bytes(self.h)
+
+    @property
+    def pyramid_stride(self) -> int:
+        return self.L.b200_pyramid_stride(self.h)
+
+    def device_hop_ring(self, nhops: int) -> _DevArray:
+        return _DevArray(self.L.b200_device_hop_ring(self.h), (nhops, self.hop_floats), "<f4", self)
+
+    def device_spectrum(self, frames: int = 1) -> _DevArray:
+        """float32 [frames][stride][2] view of the device spectrum."""
+        return _DevArray(self.L.b200_device_spectrum(self.h), (frames, self.spectrum_stride, 2), "<f4", self)
+
+    def device_quantized(self, frames: int = 1) -> _DevArray:
+        return _DevArray(self.L.b200_device_quantized(self.h), (frames, self.pyramid_stride), "|i1", self)
+
+    def execute_device(self, hop_index: int, nframes: int = 1) -> None:
+        check(self.L.b200_execute_device_batch(self.h, hop_index, nframes))
+
+    def sync(self) -> None:
+        check(self.L.b200_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return self.L.b200_stream(self.h) or 0
+
+    def bind_spectrum(self, dev_ptr: int) -> None:
+        check(self.L.b200_bind_spectrum(self.h, dev_ptr))
+
+    def set_peer_spectra(self, ptrs: Sequence[int]) -> None:
+        arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+        check(self.L.b200_set_peer_spectra(self.h, len(ptrs), arr))
+
+    def ipc_export(self, dev_ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(self.L.b200_ipc_export(self.h, dev_ptr, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        check(self.L.b200_ipc_open(self.h, buf, C.byref(out)))
+        return out.value
+
+    def ipc_close(self, dev_ptr: int) -> None:
+        check(self.L.b200_ipc_close(self.h, dev_ptr))
+
+    @property
+    def launch_count(self) -> int:
+        return self.L.b200_launch_count(self.h)
+
+    # ---- signal slot (AudioClient) -----------------------------------------------------------
+    def clients_create(self, max_clients: int, audio_fft_size: int, audio_max_sps: int) -> None:
+        check(self.L.b200_clients_create(self.h, max_clients, audio_fft_size, audio_max_sps))
+        self.max_clients = max_clients
+        self.n_audio = audio_fft_size
+
+    def client_open(self, slot: int, l: int, audio_mid: float, r: int, demodulation: int) -> None:
+        check(self.L.b200_client_open(self.h, slot, l, audio_mid, r, demodulation))
+
+    def client_set_window(self, slot: int, l: int, audio_mid: float, r: int) -> bool:
+        """AudioClient::on_window_message: returns False where the reference ignores the message."""
+        rc = self.L.b200_client_set_window(self.h, slot, l, audio_mid, r)
+        if rc == -22:
+            return False
+        check(rc)
+        return True
+
+    def client_set_demodulation(self, slot: int, demodulation: int) -> None:
+        check(self.L.b200_client_set_demodulation(self.h, slot, demodulation))
+
+    def client_close(self, slot: int) -> None:
+        check(self.L.b200_client_close(self.h, slot))
+
+    def clients_execute(self, frame_num: int):
+        """One signal_loop pass. Returns (pcm int32 [max_clients, n/2], pwr float32 [max_clients], valid uint8)."""
+        h = self.n_audio // 2
+        pcm = np.zeros((self.max_clients, h), np.int32)
+        pwr = np.zeros(self.max_clients, np.float32)
+        valid = np.zeros(self.max_clients, np.uint8)
+        check(self.L.b200_clients_execute(self.h, frame_num, _ptr(pcm), _ptr(pwr), _ptr(valid)))
+        return pcm, pwr, valid
+
+    def clients_execute_device(self, frame_num: int, nframes: int = 1) -> None:
+        check(self.L.b200_clients_execute_device(self.h, frame_num, nframes))
+
+    def clients_fetch(self, frame: int = 0, out=None):
+        h = self.n_audio // 2
+        if out is None:
+            out = (np.zeros((self.max_clients, h), np.int32), np.zeros(self.max_clients, np.float32),
+                   np.zeros(self.max_clients, np.uint8))
+        check(self.L.b200_clients_fetch(self.h, frame, _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return out
+
+    def clients_read_pre_dc(self) -> np.ndarray:
+        out = np.zeros((self.max_clients, self.n_audio // 2), np.float32)
+        check(self.L.b200_clients_read_pre_dc(self.h, _ptr(out)))
+        return out
+
+    # ---- waterfall slot ----------------------------------------------------------------------
+    def waterfall_gather(self, levels: Sequence[int], ls: Sequence[int], rs: Sequence[int]):
+        """N x send_waterfall (src/waterfall.cpp:44-51): returns one int8 array per client."""
+        n = len(levels)
+        lv = np.asarray(levels, np.int32)
+        l = np.asarray(ls, np.int32)
+        r = np.asarray(rs, np.int32)
+        lens = (r - l).astype(np.int64)
+        offs = np.zeros(n, np.uint64)
+        if n:
+            offs[1:] = np.cumsum(lens)[:-1]
+        out = np.zeros(int(lens.sum()) if n else 0, np.int8)
+        check(self.L.b200_waterfall_gather(self.h, n, _ptr(lv), _ptr(l), _ptr(r), _ptr(offs), _ptr(out)))
+        return [out[int(offs[i]): int(offs[i] + lens[i])] for i in range(n)]
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            for p in list(self._bufs.values()):
+                self.L.b200_free(self.h, p)
+            self._bufs.clear()
+            self.L.b200_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,982 @@
+// Host side of the B200 spectrum engine and its C ABI (include/phantomsdr_b200.h).
+// Mirrors the reference's FFT backend life cycle (src/fft.h:33-63, src/fft_impl.cpp:63-183,
+// src/fft_cuda.cu) and the AudioClient bookkeeping (src/signal.cpp:7-98,300-336) around the
+// kernels in fft_fwd.cuh and clients.cuh. No CPU fallback exists: every compute entry point
+// launches CUDA kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/phantomsdr_b200.h"
+#include "clients.cuh"
+#include "fft_fwd.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t err__ = (call);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            return fail(B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+struct SubPlan {  // S = RA * RB points per sub-transform, T columns per CTA
+    int S, RA, RB, T;
+};
+
+SubPlan sub_plan(int S) {
+    switch (S) {
+    case 256: return {256, 16, 16, 32};
+    case 512: return {512, 16, 32, 16};
+    case 1024: return {1024, 32, 32, 16};
+    }
+    return {0, 0, 0, 0};
+}
+
+float2 *upload_f2(const std::vector<float2> &v) {
+    float2 *d = nullptr;
+    if (cudaMalloc(&d, sizeof(float2) * v.size()) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, v.data(), sizeof(float2) * v.size(), cudaMemcpyHostToDevice);
+    return d;
+}
+
+std::vector<float2> tw_sub(int RA, int RB) {  // [q][r] = exp(-2*pi*i*r*q/S)
+    const int S = RA * RB;
+    std::vector<float2> t((size_t)RA * RB);
+    for (int q = 0; q < RA; q++)
+        for (int r = 0; r < RB; r++) {
+            const double a = -2.0 * M_PI * (double)((r * q) % S) / S;
+            t[(size_t)q * RB + r] = make_float2((float)cos(a), (float)sin(a));
+        }
+    return t;
+}
+
+std::vector<float2> tw_pow(size_t count, size_t mult, size_t N) {  // [j] = exp(-2*pi*i*(j*mult mod N)/N)
+    std::vector<float2> t(count);
+    for (size_t j = 0; j < count; j++) {
+        const double a = -2.0 * M_PI * (double)((j * mult) % N) / (double)N;
+        t[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    return t;
+}
+
+}  // namespace
+
+struct b200_engine {
+    int device = 0;
+    size_t size = 0;
+    int levels = 1;
+    int size_log2 = 0;
+    size_t additional = 0;
+    bool planned = false;
+    bool is_real = false;
+    size_t M = 0;  // complex transform length
+    int log2M = 0;
+    size_t R = 0;  // fft_result_size
+    SubPlan sp1{}, sp2{};
+    cudaStream_t stream = nullptr;
+
+    float *d_window = nullptr;
+    float2 *d_Y = nullptr, *d_Z = nullptr, *d_spec = nullptr, *spec_bound = nullptr;
+    int8_t *d_quant = nullptr;
+    float *d_ptop = nullptr;
+    float2 *d_twA1 = nullptr, *d_twA2 = nullptr, *d_TL = nullptr, *d_TH = nullptr, *d_TLr = nullptr, *d_THr = nullptr;
+    size_t spec_stride = 0, pyr_stride = 0, pyr_bytes = 0;
+    int batch = 1;
+
+    void *d_ring = nullptr;
+    size_t nhops = 3;
+    int in_format = B200_FMT_F32;
+    size_t hop_samples = 0;  // scalar samples per hop (size for c2c IQ floats, size/2 for r2c)
+
+    float *h_out = nullptr;
+    int8_t *h_quant = nullptr;
+
+    // load bookkeeping
+    const void *last_a2 = nullptr;
+    long head = -1;      // ring index of the newest hop
+    long frame_hop0 = -1;
+    int opt_reload_both = 0;
+    int opt_mirror = 3;
+
+    int npeers = 0;
+    float2 *peers[kMaxPeers] = {};
+
+    // clients
+    bool have_clients = false;
+    ClientArrays ca{};
+    std::vector<ClientSlot> slots;
+    std::vector<double> mids;
+    bool slots_dirty = true;
+    std::vector<int> order;
+    int *d_order = nullptr;
+    int tail_cpb = 32;
+    size_t tail_smem = 0;
+    int demod_wpb = 8;
+    int last_client_frames = 0;
+
+    uint64_t launches = 0;
+
+    size_t format_bytes() const {
+        switch (in_format) {
+        case B200_FMT_U8:
+        case B200_FMT_S8: return 1;
+        case B200_FMT_U16:
+        case B200_FMT_S16: return 2;
+        default: return 4;
+        }
+    }
+    size_t hop_bytes_max() const { return hop_samples * 4; }
+    float2 *spec_ptr() const { return spec_bound ? spec_bound : d_spec; }
+};
+
+namespace {
+
+template <int RA, int RB, int T> int launch_pass1(b200_engine *e, const FwdParams &p, int frames) {
+    constexpr int threads = T * CMax<RA, RB>::v;
+    constexpr int PAD = (T < 16) ? (16 - T) : 0;
+    constexpr size_t smem = sizeof(float2) * RB * (RA * T + PAD);
+    if (frames == 0) {  // preparation call from plan time
+        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    }
+    dim3 grid(p.N2 / T, frames);
+    fft_pass1_kernel<RA, RB, T><<<grid, threads, smem, e->stream>>>(p);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+template <int RA, int RB, int T> int launch_pass2(b200_engine *e, const FwdParams &p, int frames) {
+    constexpr int threads = T * CMax<RA, RB>::v;
+    constexpr size_t smem = sizeof(float2) * RB * (RA * T + 1);
+    if (frames == 0) {  // preparation call from plan time
+        CU(cudaFuncSetAttribute(fft_pass2_kernel<RA, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    }
+    dim3 grid(p.N1 / T, frames);
+    fft_pass2_kernel<RA, RB, T><<<grid, threads, smem, e->stream>>>(p);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int dispatch_pass1(b200_engine *e, const FwdParams &p, int frames) {
+    switch (e->sp1.S) {
+    case 256: return launch_pass1<16, 16, 32>(e, p, frames);
+    case 512: return launch_pass1<16, 32, 16>(e, p, frames);
+    case 1024: return launch_pass1<32, 32, 16>(e, p, frames);
+    }
+    return fail(B200_ENOTSUP, "no pass-1 kernel for sub-transform %d", e->sp1.S);
+}
+int dispatch_pass2(b200_engine *e, const FwdParams &p, int frames) {
+    switch (e->sp2.S) {
+    case 256: return launch_pass2<16, 16, 32>(e, p, frames);
+    case 512: return launch_pass2<16, 32, 16>(e, p, frames);
+    case 1024: return launch_pass2<32, 32, 16>(e, p, frames);
+    }
+    return fail(B200_ENOTSUP, "no pass-2 kernel for sub-transform %d", e->sp2.S);
+}
+
+// forward FFT + pyramid for `frames` consecutive frames starting at ring hop `hop0`
+int run_forward(b200_engine *e, long hop0, int frames) {
+    FwdParams p{};
+    p.ring = e->d_ring;
+    p.hop_bytes = e->hop_samples * e->format_bytes();
+    p.nhops = (int)e->nhops;
+    p.hop0 = (int)hop0;
+    p.in_format = e->in_format;
+    p.window = e->d_window;
+    p.Y = e->d_Y;
+    p.log2M = e->log2M;
+    p.N1 = e->sp1.S;
+    p.N2 = e->sp2.S;
+    p.is_real = e->is_real ? 1 : 0;
+    p.twA1 = e->d_twA1;
+    p.twA2 = e->d_twA2;
+    p.TL = e->d_TL;
+    p.TH = e->d_TH;
+    float2 *spec = e->spec_ptr();
+    if (!e->is_real) {
+        p.shift = 1;
+        p.out = spec;
+        p.out_stride = e->spec_stride;
+        p.scale = 1.0f / (float)e->size;
+        p.additional = (int)e->additional;
+        p.npeers = e->npeers;
+        for (int i = 0; i < e->npeers; i++) p.peers[i] = e->peers[i];
+    } else {
+        p.shift = 0;
+        p.out = e->d_Z;
+        p.out_stride = e->M;
+        p.scale = 1.0f;
+        p.additional = 0;
+        p.npeers = 0;
+    }
+    int rc = dispatch_pass1(e, p, frames);
+    if (rc) return rc;
+    rc = dispatch_pass2(e, p, frames);
+    if (rc) return rc;
+
+    PyrParams q{};
+    q.spec = spec;
+    q.spec_stride = e->spec_stride;
+    q.Z = e->d_Z;
+    q.quant = e->d_quant;
+    q.pyr_stride = e->pyr_stride;
+    q.ptop = e->d_ptop;
+    int log2R = 0;
+    while (((size_t)1 << log2R) < e->R) log2R++;
+    q.log2R = log2R;
+    q.levels = e->levels;
+    q.size_log2 = e->size_log2;
+    q.is_real = e->is_real ? 1 : 0;
+    q.scale = 1.0f / (float)e->size;
+    q.TLr = e->d_TLr;
+    q.THr = e->d_THr;
+    q.npeers = e->is_real ? e->npeers : 0;
+    for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i];
+    dim3 grid((unsigned)(e->R / 1024), frames);
+    pyramid_kernel<<<grid, 256, 0, e->stream>>>(q);
+    e->launches++;
+    CU(cudaGetLastError());
+    if (e->levels > 11) {
+        pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
+int plan_common(b200_engine *e, bool is_real) {
+    if (e->planned) return fail(B200_ESTATE, "engine already planned");
+    CU(cudaSetDevice(e->device));
+    e->is_real = is_real;
+    e->M = is_real ? e->size / 2 : e->size;
+    e->R = is_real ? e->size / 2 : e->size;
+    e->log2M = 0;
+    while (((size_t)1 << e->log2M) < e->M) e->log2M++;
+    int s1 = 0, s2 = 0;
+    switch (e->log2M) {
+    case 16: s1 = 256; s2 = 256; break;
+    case 17: s1 = 512; s2 = 256; break;
+    case 18: s1 = 512; s2 = 512; break;
+    case 19: s1 = 1024; s2 = 512; break;
+    case 20: s1 = 1024; s2 = 1024; break;
+    default:
+        return fail(B200_ENOTSUP, "fft size %zu (%s) not supported: complex transform length must be 2^16..2^20", e->size,
+                    is_real ? "r2c" : "c2c");
+    }
+    e->sp1 = sub_plan(s1);
+    e->sp2 = sub_plan(s2);
+    if (e->levels < 1) return fail(B200_EINVAL, "downsample_levels must be >= 1");
+    if ((e->R >> (e->levels - 1)) < 1) return fail(B200_EINVAL, "too many downsample levels for %zu bins", e->R);
+    e->hop_samples = is_real ? e->size / 2 : e->size;  // scalar samples per hop
+    e->spec_stride = is_real ? (e->size / 2 + 8) : (e->size + ((e->additional + 7) & ~(size_t)7) + 8);
+    e->pyr_bytes = 0;
+    for (int i = 0; i < e->levels; i++) e->pyr_bytes += e->R >> i;
+    e->pyr_stride = (e->pyr_bytes + 255) & ~(size_t)255;
+
+    // twiddles (double precision on the host, rounded once)
+    e->d_twA1 = upload_f2(tw_sub(e->sp1.RA, e->sp1.RB));
+    e->d_twA2 = upload_f2(tw_sub(e->sp2.RA, e->sp2.RB));
+    e->d_TL = upload_f2(tw_pow(1024, 1, e->M));
+    e->d_TH = upload_f2(tw_pow(std::max<size_t>(1, e->M / 1024), 1024, e->M));
+    if (is_real) {
+        e->d_TLr = upload_f2(tw_pow(1024, 1, e->size));
+        e->d_THr = upload_f2(tw_pow(std::max<size_t>(1, e->M / 1024), 1024, e->size));
+    }
+    if (!e->d_twA1 || !e->d_twA2 || !e->d_TL || !e->d_TH) return fail(B200_ENOMEM, "twiddle allocation failed");
+
+    // pinned host mirrors (FFT::get_output_buffer / get_quantized_buffer must be CPU-readable)
+    const size_t out_floats = is_real ? e->size + 2 : 2 * (e->size + e->additional);
+    CU(cudaHostAlloc(&e->h_out, sizeof(float) * out_floats, cudaHostAllocDefault));
+    memset(e->h_out, 0, sizeof(float) * out_floats);
+    CU(cudaHostAlloc(&e->h_quant, e->pyr_stride, cudaHostAllocDefault));
+    memset(e->h_quant, 0, e->pyr_stride);
+    {   // opt the chosen kernels into their shared-memory footprint on this device
+        FwdParams none{};
+        int rc = dispatch_pass1(e, none, 0);
+        if (rc) return rc;
+        rc = dispatch_pass2(e, none, 0);
+        if (rc) return rc;
+    }
+    e->planned = true;
+    return 0;
+}
+
+int alloc_batch(b200_engine *e, int frames) {
+    if (e->d_Y) cudaFree(e->d_Y);
+    if (e->d_Z) cudaFree(e->d_Z);
+    if (e->d_spec) cudaFree(e->d_spec);
+    if (e->d_quant) cudaFree(e->d_quant);
+    if (e->d_ptop) cudaFree(e->d_ptop);
+    e->d_Y = e->d_Z = e->d_spec = nullptr;
+    e->d_quant = nullptr;
+    e->d_ptop = nullptr;
+    CU(cudaMalloc(&e->d_Y, sizeof(float2) * e->M * frames));
+    if (e->is_real) CU(cudaMalloc(&e->d_Z, sizeof(float2) * e->M * frames));
+    CU(cudaMalloc(&e->d_spec, sizeof(float2) * e->spec_stride * frames));
+    CU(cudaMemset(e->d_spec, 0, sizeof(float2) * e->spec_stride * frames));
+    CU(cudaMalloc(&e->d_quant, e->pyr_stride * frames));
+    CU(cudaMemset(e->d_quant, 0, e->pyr_stride * frames));
+    CU(cudaMalloc(&e->d_ptop, sizeof(float) * std::max<size_t>(1, e->R / 1024) * frames));
+    e->batch = frames;
+    return 0;
+}
+
+int alloc_ring(b200_engine *e, size_t nhops) {
+    if (e->d_ring) cudaFree(e->d_ring);
+    e->d_ring = nullptr;
+    CU(cudaMalloc(&e->d_ring, e->hop_bytes_max() * nhops));
+    CU(cudaMemset(e->d_ring, 0, e->hop_bytes_max() * nhops));
+    e->nhops = nhops;
+    e->head = -1;
+    e->last_a2 = nullptr;
+    e->frame_hop0 = -1;
+    return 0;
+}
+
+int load_common(b200_engine *e, const void *a1, const void *a2) {
+    if (!e->planned) return fail(B200_ESTATE, "load before plan");
+    if (!a1 || !a2) return fail(B200_EINVAL, "null input half");
+    CU(cudaSetDevice(e->device));
+    const size_t hb = e->hop_samples * e->format_bytes();
+    char *ring = reinterpret_cast<char *>(e->d_ring);
+    long hopA, hopB;
+    if (e->head >= 0 && a1 == e->last_a2 && !e->opt_reload_both) {
+        hopA = e->head;
+        hopB = (e->head + 1) % (long)e->nhops;
+    } else {
+        hopA = (e->head + 1) % (long)e->nhops;
+        hopB = (hopA + 1) % (long)e->nhops;
+        CU(cudaMemcpyAsync(ring + (size_t)hopA * hb, a1, hb, cudaMemcpyHostToDevice, e->stream));
+    }
+    CU(cudaMemcpyAsync(ring + (size_t)hopB * hb, a2, hb, cudaMemcpyHostToDevice, e->stream));
+    e->head = hopB;
+    e->last_a2 = a2;
+    e->frame_hop0 = hopA;
+    return 0;
+}
+
+std::vector<int> factorize(int n) {
+    std::vector<int> r;
+    while (n % 4 == 0) { r.push_back(4); n /= 4; }
+    while (n % 2 == 0) { r.push_back(2); n /= 2; }
+    for (int p = 3; n > 1; p += 2)
+        while (n % p == 0) { r.push_back(p); n /= p; }
+    return r;
+}
+
+template <int WPB> int launch_demod(b200_engine *e, const ClientLaunch &cl) {
+    const size_t smem = sizeof(float2) * 2 * e->ca.n * WPB;
+    if (cl.nactive == 0) {  // preparation call from clients_create
+        CU(cudaFuncSetAttribute(client_demod_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    }
+    const int blocks = (cl.nactive + WPB - 1) / WPB;
+    client_demod_kernel<WPB><<<blocks, WPB * 32, smem, e->stream>>>(e->ca, cl);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
+    if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
+    if (!e->planned) return fail(B200_ESTATE, "engine not planned");
+    if (nframes < 1 || nframes > e->batch) return fail(B200_EINVAL, "nframes %d outside 1..%d", nframes, e->batch);
+    CU(cudaSetDevice(e->device));
+    if (e->slots_dirty) {
+        e->order.clear();
+        for (int i = 0; i < (int)e->slots.size(); i++)
+            if (e->slots[i].flags & CF_ACTIVE) e->order.push_back(i);
+        // std::multimap<std::pair<int,int>, ...> iteration order (src/spectrumserver.h:164-165)
+        std::stable_sort(e->order.begin(), e->order.end(), [&](int a, int b) {
+            if (e->slots[a].l != e->slots[b].l) return e->slots[a].l < e->slots[b].l;
+            return e->slots[a].r < e->slots[b].r;
+        });
+        CU(cudaMemcpyAsync(e->ca.slots, e->slots.data(), sizeof(ClientSlot) * e->slots.size(), cudaMemcpyHostToDevice,
+                           e->stream));
+        if (!e->order.empty())
+            CU(cudaMemcpyAsync(e->d_order, e->order.data(), sizeof(int) * e->order.size(), cudaMemcpyHostToDevice,
+                               e->stream));
+        // pageable source: the runtime stages it before returning, so host vectors may change afterwards
+        e->slots_dirty = false;
+    }
+    e->last_client_frames = nframes;
+    // closed slots read back as invalid
+    CU(cudaMemsetAsync(e->ca.valid, 0, (size_t)e->ca.max_clients * nframes, e->stream));
+    if (e->order.empty()) return 0;
+    ClientLaunch cl{};
+    cl.spec = e->spec_ptr();
+    cl.spec_stride = e->spec_stride;
+    cl.nframes = nframes;
+    cl.frame_num0 = frame_num;
+    cl.fft_size = e->size;
+    cl.is_real = e->is_real ? 1 : 0;
+    cl.order = e->d_order;
+    cl.nactive = (int)e->order.size();
+    cl.cpb = e->tail_cpb;
+    int rc;
+    switch (e->demod_wpb) {
+    case 8: rc = launch_demod<8>(e, cl); break;
+    case 4: rc = launch_demod<4>(e, cl); break;
+    case 2: rc = launch_demod<2>(e, cl); break;
+    default: rc = launch_demod<1>(e, cl); break;
+    }
+    if (rc) return rc;
+    const int blocks = (cl.nactive + cl.cpb - 1) / cl.cpb;
+    client_tail_kernel<<<blocks, kTailThreads, e->tail_smem, e->stream>>>(e->ca, cl);
+    e->launches++;
+    CU(cudaGetLastError());
+    // one-shot reset flags have been consumed by this launch
+    bool any = false;
+    for (auto &s : e->slots)
+        if (s.flags & (CF_RESET_AGC | CF_RESET_ALL)) {
+            s.flags &= ~(CF_RESET_AGC | CF_RESET_ALL);
+            any = true;
+        }
+    if (any) e->slots_dirty = true;
+    return 0;
+}
+
+__global__ void waterfall_gather_kernel(const int8_t *quant, const size_t *src_off, const int *len, const size_t *dst_off,
+                                        int8_t *out) {
+    const int c = blockIdx.x;
+    const int8_t *s = quant + src_off[c];
+    int8_t *d = out + dst_off[c];
+    for (int i = threadIdx.x; i < len[c]; i += blockDim.x) d[i] = s[i];
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI (the only symbols the library exports)
+// ================================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+const char *b200_last_error(void) { return g_err; }
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b200_engine_create(b200_engine **out, size_t size, int nthreads, int downsample_levels, int brightness_offset,
+                       int device) {
+    (void)nthreads;
+    if (!out) return fail(B200_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (size < 2 || (size & (size - 1))) return fail(B200_ENOTSUP, "fft size %zu is not a power of two", size);
+    int count = b200_device_count();
+    if (count == 0) return fail(B200_ENODEV, "No CUDA devices found");  // src/fft_cuda.cu:10-13
+    if (device < 0 || device >= count) return fail(B200_ENODEV, "device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    b200_engine *e = new b200_engine();
+    e->device = device;
+    e->size = size;
+    e->levels = downsample_levels;
+    e->size_log2 = (int)round(log2((double)size)) + brightness_offset;  // src/fft_impl.cpp:68
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+        delete e;
+        return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
+    }
+    // Hann window built on the host exactly like build_hann_window (src/utils/dsp.cpp:6-11) and uploaded,
+    // as the reference's own CUDA backend does (src/fft_cuda.cu:15-17)
+    std::vector<float> w(size);
+    const int num = (int)size;
+    for (int i = 0; i < num; i++) w[i] = 0.5 * (1 - cosf(2 * M_PI * i / num));
+    err = cudaMalloc(&e->d_window, sizeof(float) * size);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_window, w.data(), sizeof(float) * size, cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+        b200_engine_destroy(e);
+        return fail(B200_ECUDA, "window upload failed: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return 0;
+}
+
+void b200_engine_destroy(b200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec, e->d_quant, e->d_ptop, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
+                   e->d_TLr, e->d_THr, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
+                   e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
+                   e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
+                   e->ca.pwr, e->ca.pcm, e->ca.valid};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->h_quant) cudaFreeHost(e->h_quant);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int b200_set_output_additional_size(b200_engine *e, size_t n) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (e->planned) return fail(B200_ESTATE, "set_output_additional_size after plan");
+    e->additional = n;
+    return 0;
+}
+
+float *b200_malloc(b200_engine *e, size_t nfloats) {
+    if (!e) return nullptr;
+    cudaSetDevice(e->device);
+    float *p = nullptr;
+    if (cudaHostAlloc(&p, sizeof(float) * nfloats, cudaHostAllocDefault) != cudaSuccess) {
+        fail(B200_ENOMEM, "cudaHostAlloc of %zu floats failed", nfloats);
+        return nullptr;
+    }
+    return p;
+}
+void b200_free(b200_engine *e, float *buf) {
+    if (!e || !buf) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->last_a2 == buf) e->last_a2 = nullptr;
+    cudaFreeHost(buf);
+}
+
+int b200_plan_c2c(b200_engine *e, int direction, int options) {
+    (void)options;
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (direction != B200_FORWARD) return fail(B200_ENOTSUP, "only the forward transform is on this path (src/fft.cpp:28)");
+    int rc = plan_common(e, false);
+    if (rc) return rc;
+    rc = alloc_batch(e, 1);
+    if (rc) return rc;
+    return alloc_ring(e, 3);
+}
+int b200_plan_r2c(b200_engine *e, int options) {
+    (void)options;
+    if (!e) return fail(B200_EINVAL, "null engine");
+    int rc = plan_common(e, true);
+    if (rc) return rc;
+    rc = alloc_batch(e, 1);
+    if (rc) return rc;
+    return alloc_ring(e, 3);
+}
+
+float *b200_get_output_buffer(b200_engine *e) { return e ? e->h_out : nullptr; }
+int8_t *b200_get_quantized_buffer(b200_engine *e) { return e ? e->h_quant : nullptr; }
+
+int b200_load_real_input(b200_engine *e, const float *a1, const float *a2) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->is_real) return fail(B200_ESTATE, "load_real_input on a c2c plan");
+    if (e->in_format != B200_FMT_F32) {
+        e->in_format = B200_FMT_F32;
+        e->last_a2 = nullptr;
+    }
+    return load_common(e, a1, a2);
+}
+int b200_load_complex_input(b200_engine *e, const float *a1, const float *a2) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (e->is_real) return fail(B200_ESTATE, "load_complex_input on an r2c plan");
+    if (e->in_format != B200_FMT_F32) {
+        e->in_format = B200_FMT_F32;
+        e->last_a2 = nullptr;
+    }
+    return load_common(e, a1, a2);
+}
+int b200_load_raw_input(b200_engine *e, const void *a1, const void *a2) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    return load_common(e, a1, a2);
+}
+
+int b200_set_option(b200_engine *e, int option, int value) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    switch (option) {
+    case B200_OPT_RELOAD_BOTH: e->opt_reload_both = value ? 1 : 0; return 0;
+    case B200_OPT_HOST_MIRROR: e->opt_mirror = value & 3; return 0;
+    case B200_OPT_INPUT_FORMAT:
+        if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
+        if (value != e->in_format) {
+            e->in_format = value;
+            e->last_a2 = nullptr;  // ring contents are in the old format
+            e->head = -1;
+        }
+        return 0;
+    }
+    return fail(B200_EINVAL, "unknown option %d", option);
+}
+
+int b200_execute(b200_engine *e) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "execute before plan");
+    if (e->frame_hop0 < 0) return fail(B200_ESTATE, "execute before load_*_input");
+    CU(cudaSetDevice(e->device));
+    int rc = run_forward(e, e->frame_hop0, 1);
+    if (rc) return rc;
+    if (e->opt_mirror & 1) {
+        const size_t bins = e->is_real ? e->size / 2 + 1 : e->size + e->additional;
+        CU(cudaMemcpyAsync(e->h_out, e->spec_ptr(), sizeof(float2) * bins, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (e->opt_mirror & 2)
+        CU(cudaMemcpyAsync(e->h_quant, e->d_quant, e->pyr_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+void *b200_device_spectrum(b200_engine *e) { return e ? e->spec_ptr() : nullptr; }
+void *b200_device_quantized(b200_engine *e) { return e ? e->d_quant : nullptr; }
+void *b200_device_hop_ring(b200_engine *e) { return e ? e->d_ring : nullptr; }
+size_t b200_hop_floats(b200_engine *e) { return e ? e->hop_samples : 0; }
+size_t b200_spectrum_bins(b200_engine *e) {
+    if (!e) return 0;
+    return e->is_real ? e->size / 2 + 1 : e->size + e->additional;
+}
+size_t b200_pyramid_bytes(b200_engine *e) { return e ? e->pyr_bytes : 0; }
+size_t b200_spectrum_stride(b200_engine *e) { return e ? e->spec_stride : 0; }
+size_t b200_pyramid_stride(b200_engine *e) { return e ? e->pyr_stride : 0; }
+
+int b200_set_hop_ring(b200_engine *e, size_t nhops) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "set_hop_ring before plan");
+    if (nhops < 2) return fail(B200_EINVAL, "hop ring needs at least 2 hops");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return alloc_ring(e, nhops);
+}
+int b200_set_batch_frames(b200_engine *e, int max_frames) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "set_batch_frames before plan");
+    if (e->have_clients) return fail(B200_ESTATE, "set_batch_frames must precede clients_create");
+    if (max_frames < 1 || max_frames > 64) return fail(B200_EINVAL, "batch frames must be 1..64");
+    if (e->spec_bound) return fail(B200_ESTATE, "spectrum is bound to an external buffer");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return alloc_batch(e, max_frames);
+}
+int b200_execute_device_batch(b200_engine *e, size_t hop_index, int nframes) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "execute before plan");
+    if (nframes < 1 || nframes > e->batch) return fail(B200_EINVAL, "nframes %d outside 1..%d", nframes, e->batch);
+    if (hop_index >= e->nhops) return fail(B200_EINVAL, "hop index %zu outside ring of %zu", hop_index, e->nhops);
+    CU(cudaSetDevice(e->device));
+    return run_forward(e, (long)hop_index, nframes);
+}
+int b200_execute_device(b200_engine *e, size_t hop_index) { return b200_execute_device_batch(e, hop_index, 1); }
+int b200_sync(b200_engine *e) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+void *b200_stream(b200_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+int b200_bind_spectrum(b200_engine *e, void *dev_ptr) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "bind_spectrum before plan");
+    e->spec_bound = reinterpret_cast<float2 *>(dev_ptr);
+    return 0;
+}
+int b200_set_peer_spectra(b200_engine *e, int npeers, void *const *dev_ptrs) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (npeers < 0 || npeers > kMaxPeers) return fail(B200_EINVAL, "npeers must be 0..%d", kMaxPeers);
+    e->npeers = npeers;
+    for (int i = 0; i < npeers; i++) e->peers[i] = reinterpret_cast<float2 *>(dev_ptrs[i]);
+    return 0;
+}
+int b200_ipc_export(b200_engine *e, const void *dev_ptr, uint8_t handle[64]) {
+    if (!e || !dev_ptr || !handle) return fail(B200_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return 0;
+}
+int b200_ipc_open(b200_engine *e, const uint8_t handle[64], void **dev_ptr) {
+    if (!e || !dev_ptr || !handle) return fail(B200_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int b200_ipc_close(b200_engine *e, void *dev_ptr) {
+    if (!e || !dev_ptr) return fail(B200_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// signal slot group
+// ------------------------------------------------------------------------------------------------
+int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int audio_max_sps) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "clients_create before plan");
+    if (e->have_clients) return fail(B200_ESTATE, "clients already created");
+    if (max_clients < 1) return fail(B200_EINVAL, "max_clients must be >= 1");
+    if (audio_fft_size < 4 || audio_fft_size % 4) return fail(B200_EINVAL, "audio_fft_size must be a positive multiple of 4");
+    if (!e->is_real && (size_t)audio_fft_size > e->additional)
+        return fail(B200_EINVAL, "output additional size %zu < audio_fft_size %d (src/spectrumserver.cpp:214)",
+                    e->additional, audio_fft_size);
+    CU(cudaSetDevice(e->device));
+    ClientArrays &ca = e->ca;
+    ca.n = audio_fft_size;
+    ca.h = audio_fft_size / 2;
+    ca.D = audio_max_sps / 750 * 2;  // DCBlocker<float>(audio_max_sps / 750 * 2), src/signal.cpp:54
+    if (ca.D < 1) return fail(B200_EINVAL, "audio_max_sps %d gives an empty DC blocker", audio_max_sps);
+    // AGC(0.2f, 50.0f, 300.0f, 200.0f, audio_max_sps), src/signal.cpp:55, src/utils/audioprocessing.cpp:5-15
+    const float sr = (float)audio_max_sps;
+    ca.L = (int)static_cast<size_t>(200.0f * sr / 1000.0f);
+    ca.attack = (float)(1 - exp((double)(-1.0f / (50.0f * 0.001f * sr))));
+    ca.release = (float)(1 - exp((double)(-1.0f / (300.0f * 0.001f * sr))));
+    ca.desired = 0.2f;
+    if (ca.L < ca.h + 1)
+        return fail(B200_ENOTSUP, "AGC look-ahead (%d samples) shorter than one frame of audio (%d): not supported", ca.L,
+                    ca.h);
+    ca.NC = (ca.L - 1 + ca.h - 1) / ca.h + 2;
+    ca.max_clients = max_clients;
+    std::vector<int> rad = factorize(audio_fft_size);
+    if ((int)rad.size() > kMaxStages) return fail(B200_ENOTSUP, "audio_fft_size has too many factors");
+    ca.nstages = (int)rad.size();
+    for (int i = 0; i < ca.nstages; i++) ca.radix[i] = rad[i];
+    {
+        std::vector<float2> wn(audio_fft_size);
+        for (int k = 0; k < audio_fft_size; k++) {
+            const double a = 2.0 * M_PI * (double)k / audio_fft_size;
+            wn[k] = make_float2((float)cos(a), (float)sin(a));
+        }
+        ca.Wn = upload_f2(wn);
+        if (!ca.Wn) return fail(B200_ENOMEM, "twiddle allocation failed");
+    }
+    const size_t mc = max_clients, h = ca.h, F = e->batch;
+#define ALLOC0(ptr, bytes)                        \
+    CU(cudaMalloc((void **)&(ptr), (bytes)));     \
+    CU(cudaMemset((ptr), 0, (bytes)))
+    ALLOC0(ca.slots, sizeof(ClientSlot) * mc);
+    ALLOC0(ca.real_prev, sizeof(float) * mc * h);
+    ALLOC0(ca.real_hi, sizeof(float) * mc * h);
+    ALLOC0(ca.hi_diverged, sizeof(int) * mc);
+    ALLOC0(ca.bb_hi, sizeof(float2) * mc * h);
+    ALLOC0(ca.bb_last, sizeof(float2) * mc);
+    ALLOC0(ca.dc_x, sizeof(float) * mc * ca.D);
+    ALLOC0(ca.dc_m, sizeof(float) * mc * ca.D);
+    ALLOC0(ca.dc_sum, sizeof(float) * mc * 2);
+    ALLOC0(ca.agc_ring, sizeof(float) * mc * ca.NC * h);
+    ALLOC0(ca.agc_cmax, sizeof(float) * mc * ca.NC);
+    ALLOC0(ca.agc_gain, sizeof(float) * mc);
+    ALLOC0(ca.agc_t0, sizeof(long long) * mc);
+    ALLOC0(ca.audio_pre, sizeof(float) * F * mc * h);
+    ALLOC0(ca.valid_a, F * mc);
+    ALLOC0(ca.pwr, sizeof(float) * F * mc);
+    ALLOC0(ca.pcm, sizeof(int) * F * mc * h);
+    ALLOC0(ca.valid, F * mc);
+    ALLOC0(e->d_order, sizeof(int) * mc);
+#undef ALLOC0
+    e->slots.assign(mc, ClientSlot{});
+    e->mids.assign(mc, 0.0);
+    // launch geometry
+    e->demod_wpb = 8;
+    while (e->demod_wpb > 1 && sizeof(float2) * 2 * ca.n * e->demod_wpb > 160 * 1024) e->demod_wpb /= 2;
+    if (sizeof(float2) * 2 * ca.n > 200 * 1024) return fail(B200_ENOTSUP, "audio_fft_size %d too large", ca.n);
+    e->tail_cpb = 32;
+    auto tail_bytes = [&](int cpb) { return sizeof(float) * (size_t)(7 * ca.h + 2 * ca.D) * (cpb + 1); };
+    while (e->tail_cpb > 1 && tail_bytes(e->tail_cpb) > 200 * 1024) e->tail_cpb /= 2;
+    if (tail_bytes(e->tail_cpb) > 200 * 1024) return fail(B200_ENOTSUP, "audio_fft_size %d too large for the tail kernel", ca.n);
+    e->tail_smem = tail_bytes(e->tail_cpb);
+    CU(cudaFuncSetAttribute(client_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tail_smem));
+    {
+        ClientLaunch none{};
+        int rc;
+        switch (e->demod_wpb) {
+        case 8: rc = launch_demod<8>(e, none); break;
+        case 4: rc = launch_demod<4>(e, none); break;
+        case 2: rc = launch_demod<2>(e, none); break;
+        default: rc = launch_demod<1>(e, none); break;
+        }
+        if (rc) return rc;
+    }
+    e->have_clients = true;
+    e->slots_dirty = true;
+    return 0;
+}
+
+static int check_slot(b200_engine *e, int slot) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
+    if (slot < 0 || slot >= e->ca.max_clients) return fail(B200_EINVAL, "slot %d out of range", slot);
+    return 0;
+}
+static int window_ok(b200_engine *e, int l, int r) {
+    // AudioClient::on_window_message, src/signal.cpp:300-314
+    const int R = (int)e->R;
+    if (l < 0 || l >= R || r < 0 || r >= R || l > r) return 0;
+    if (r - l > e->ca.n) return 0;
+    return 1;
+}
+
+int b200_client_open(b200_engine *e, int slot, int l, double audio_mid, int r, int demodulation) {
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    if (demodulation < B200_USB || demodulation > B200_FM) return fail(B200_EINVAL, "unknown demodulation %d", demodulation);
+    if (!window_ok(e, l, r)) return fail(B200_EINVAL, "window [%d, %d) rejected (src/signal.cpp:304-311)", l, r);
+    ClientSlot &s = e->slots[slot];
+    s.l = l;
+    s.r = r;
+    s.m_floor = (int)floor(audio_mid);
+    s.mode = demodulation;
+    s.flags = CF_ACTIVE | CF_RESET_ALL;
+    e->mids[slot] = audio_mid;
+    e->slots_dirty = true;
+    return 0;
+}
+int b200_client_set_window(b200_engine *e, int slot, int l, double audio_mid, int r) {
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    if (!(e->slots[slot].flags & CF_ACTIVE)) return fail(B200_ESTATE, "slot %d is closed", slot);
+    if (!window_ok(e, l, r)) return fail(B200_EINVAL, "window [%d, %d) rejected (src/signal.cpp:304-311)", l, r);
+    ClientSlot &s = e->slots[slot];
+    s.l = l;
+    s.r = r;
+    s.m_floor = (int)floor(audio_mid);
+    e->mids[slot] = audio_mid;
+    e->slots_dirty = true;
+    return 0;
+}
+int b200_client_set_demodulation(b200_engine *e, int slot, int demodulation) {
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    if (!(e->slots[slot].flags & CF_ACTIVE)) return fail(B200_ESTATE, "slot %d is closed", slot);
+    ClientSlot &s = e->slots[slot];
+    // unknown strings leave the mode unchanged but still reset the AGC (src/signal.cpp:316-328)
+    if (demodulation >= B200_USB && demodulation <= B200_FM) s.mode = demodulation;
+    s.flags |= CF_RESET_AGC;
+    e->slots_dirty = true;
+    return 0;
+}
+int b200_client_close(b200_engine *e, int slot) {
+    int rc = check_slot(e, slot);
+    if (rc) return rc;
+    e->slots[slot].flags = 0;
+    e->slots_dirty = true;
+    return 0;
+}
+
+int b200_clients_execute_device(b200_engine *e, uint64_t frame_num, int nframes) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    return run_clients(e, frame_num, nframes);
+}
+
+int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_out, uint8_t *valid_out) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
+    if (frame < 0 || frame >= e->batch) return fail(B200_EINVAL, "frame %d outside batch", frame);
+    CU(cudaSetDevice(e->device));
+    const size_t mc = e->ca.max_clients, h = e->ca.h;
+    if (pcm_out)
+        CU(cudaMemcpyAsync(pcm_out, e->ca.pcm + (size_t)frame * mc * h, sizeof(int32_t) * mc * h, cudaMemcpyDeviceToHost,
+                           e->stream));
+    if (pwr_out)
+        CU(cudaMemcpyAsync(pwr_out, e->ca.pwr + (size_t)frame * mc, sizeof(float) * mc, cudaMemcpyDeviceToHost, e->stream));
+    if (valid_out)
+        CU(cudaMemcpyAsync(valid_out, e->ca.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int b200_clients_execute(b200_engine *e, uint64_t frame_num, int32_t *pcm_out, float *pwr_out, uint8_t *valid_out) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    int rc = run_clients(e, frame_num, 1);
+    if (rc) return rc;
+    return b200_clients_fetch(e, 0, pcm_out, pwr_out, valid_out);
+}
+
+void *b200_device_pcm(b200_engine *e) { return e ? e->ca.pcm : nullptr; }
+void *b200_device_pwr(b200_engine *e) { return e ? e->ca.pwr : nullptr; }
+void *b200_device_valid(b200_engine *e) { return e ? e->ca.valid : nullptr; }
+
+int b200_clients_read_pre_dc(b200_engine *e, float *out) {
+    if (!e || !out) return fail(B200_EINVAL, "null argument");
+    if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
+    CU(cudaSetDevice(e->device));
+    CU(cudaMemcpyAsync(out, e->ca.audio_pre, sizeof(float) * (size_t)e->ca.max_clients * e->ca.h, cudaMemcpyDeviceToHost,
+                       e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// waterfall slot group
+// ------------------------------------------------------------------------------------------------
+int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const int *l, const int *r,
+                          const size_t *out_offsets, int8_t *out) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "waterfall_gather before plan");
+    if (nclients <= 0) return 0;
+    if (!level || !l || !r || !out_offsets || !out) return fail(B200_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    std::vector<size_t> src(nclients), dst(nclients);
+    std::vector<int> len(nclients);
+    size_t total = 0;
+    for (int i = 0; i < nclients; i++) {
+        if (level[i] < 0 || level[i] >= e->levels) return fail(B200_EINVAL, "client %d: level %d out of range", i, level[i]);
+        const size_t width = e->R >> level[i];
+        if (l[i] < 0 || r[i] < l[i] || (size_t)r[i] > width)
+            return fail(B200_EINVAL, "client %d: slice [%d, %d) outside level %d", i, l[i], r[i], level[i]);
+        size_t off = 0;  // src/websocket.cpp:233: fft_power_quantized += (fft_result_size >> i)
+        for (int j = 0; j < level[i]; j++) off += e->R >> j;
+        src[i] = off + l[i];
+        len[i] = r[i] - l[i];
+        dst[i] = out_offsets[i];
+        total = std::max(total, dst[i] + (size_t)len[i]);
+    }
+    size_t *d_src = nullptr, *d_dst = nullptr;
+    int *d_len = nullptr;
+    int8_t *d_out = nullptr;
+    std::vector<int8_t> staged(std::max<size_t>(total, 1));
+    CU(cudaMalloc(&d_src, sizeof(size_t) * nclients));
+    CU(cudaMalloc(&d_dst, sizeof(size_t) * nclients));
+    CU(cudaMalloc(&d_len, sizeof(int) * nclients));
+    CU(cudaMalloc(&d_out, staged.size()));
+    CU(cudaMemcpyAsync(d_src, src.data(), sizeof(size_t) * nclients, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_dst, dst.data(), sizeof(size_t) * nclients, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(d_len, len.data(), sizeof(int) * nclients, cudaMemcpyHostToDevice, e->stream));
+    waterfall_gather_kernel<<<nclients, 256, 0, e->stream>>>(e->d_quant, d_src, d_len, d_dst, d_out);
+    e->launches++;
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(staged.data(), d_out, staged.size(), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_src);
+    cudaFree(d_dst);
+    cudaFree(d_len);
+    cudaFree(d_out);
+    if (err != cudaSuccess) return fail(B200_ECUDA, "waterfall gather failed: %s", cudaGetErrorString(err));
+    // only the clients' own byte ranges of `out` are touched
+    for (int i = 0; i < nclients; i++) memcpy(out + dst[i], staged.data() + dst[i], (size_t)len[i]);
+    return 0;
+}
+
+uint64_t b200_launch_count(b200_engine *e) { return e ? e->launches : 0; }
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,368 @@
+// Forward spectrum path: fused {sample convert, Hann window, four-step FFT pass 1}, FFT pass 2 with
+// 1/N normalisation + wrap tail + optional NVLink peer stores, and the waterfall quantiser/pyramid.
+//
+// Replaces FFTW::load_*_input + fftwf_execute + power_and_quantize + half_and_quantize
+// (reference src/fft_impl.cpp:119-174) and cuFFT's window_* / power_and_quantize /
+// half_and_quantize kernels (src/fft_cuda.cu:62-130).
+//
+// Decomposition of the M-point complex transform (M = size for c2c, size/2 for r2c packing):
+//   M = N1*N2,  n = N2*n1 + n2,  k = k1 + N1*k2
+//   pass 1: per column n2, N1-point DFT over n1, times W_M^(n2*k1)      -> Y[u1][n2]
+//   pass 2: per row   k1, N2-point DFT over n2                          -> X[k1 + N1*k2]
+// Each sub-DFT of S = RA*RB points runs on max(RA,RB) threads: an RA-point register DFT, one
+// shared-memory exchange, an RB-point register DFT. A CTA carries T adjacent columns (rows) so that
+// every global access is a run of T consecutive complex values (T*8 bytes).
+//
+// IQ display shift (src/fft_impl.cpp:148-160, base_idx = N/2+1): rows of Y are stored by
+// u1 = (k1 - shift) mod N1 and, for IQ, the k1 = 0 row is pre-rotated by W_N2^(n2) so that slot u2 of
+// that row holds k2 = u2+1. With u = u1 + N1*u2 the bin is k = (u + shift) mod M everywhere.
+#pragma once
+#include <cstdint>
+#include "regfft.cuh"
+
+namespace b200 {
+
+enum { FMT_F32 = 0, FMT_U8 = 1, FMT_S8 = 2, FMT_U16 = 3, FMT_S16 = 4 };
+
+constexpr int kMaxPeers = 8;
+
+struct FwdParams {
+    const void *ring;        // device hop ring, nhops hops
+    size_t hop_bytes;        // bytes per hop in the ring
+    int nhops;
+    int hop0;                // frame f is made of hops (hop0+f) % nhops and (hop0+f+1) % nhops
+    int in_format;           // FMT_*
+    const float *window;     // size floats (Hann, host-built)
+    float2 *Y;               // [frames][N1][N2] intermediate
+    float2 *out;             // pass 2 output: spectrum (c2c) or Z scratch (r2c)
+    size_t out_stride;       // float2 per frame in `out`
+    int log2M, N1, N2;
+    int shift;               // 1 = IQ display shift, 0 = none
+    int is_real;
+    float scale;             // applied by pass 2 (c2c: 1/size; r2c: 1)
+    int additional;          // wrap tail bins (c2c)
+    const float2 *twA1;      // [RA][RB] W_N1^(r*q)
+    const float2 *twA2;      // [RA][RB] W_N2^(r*q)
+    const float2 *TL;        // W_M^j, j < 1024
+    const float2 *TH;        // W_M^(1024 j)
+    int npeers;
+    float2 *peers[kMaxPeers];  // extra spectrum destinations (NVLink peer memory)
+};
+
+template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
+
+__device__ __forceinline__ float2 load_sample(const void *hop, int fmt, size_t e) {
+    // element e of a hop as a float pair (IQ sample, or two consecutive real samples)
+    if (fmt == FMT_F32) return reinterpret_cast<const float2 *>(hop)[e];
+    if (fmt == FMT_U8) {  // src/samplereader.cpp:29-40: (x ^ 0x80) as int8, / 128
+        uchar2 b = reinterpret_cast<const uchar2 *>(hop)[e];
+        return make_float2((float)(int8_t)(b.x ^ 0x80) / 128.0f, (float)(int8_t)(b.y ^ 0x80) / 128.0f);
+    }
+    if (fmt == FMT_S8) {
+        char2 b = reinterpret_cast<const char2 *>(hop)[e];
+        return make_float2((float)b.x / 128.0f, (float)b.y / 128.0f);
+    }
+    if (fmt == FMT_U16) {
+        ushort2 b = reinterpret_cast<const ushort2 *>(hop)[e];
+        return make_float2((float)(int16_t)(b.x ^ 0x8000) / 32768.0f, (float)(int16_t)(b.y ^ 0x8000) / 32768.0f);
+    }
+    short2 b = reinterpret_cast<const short2 *>(hop)[e];
+    return make_float2((float)b.x / 32768.0f, (float)b.y / 32768.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: grid (N2/T, frames), block T*max(RA,RB)
+// ------------------------------------------------------------------------------------------------
+template <int RA, int RB, int T>
+__global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const FwdParams p) {
+    constexpr int TPC = CMax<RA, RB>::v;
+    constexpr int PAD = (T < 16) ? (16 - T) : 0;   // keep the two r-rows of a half-warp on disjoint banks
+    constexpr int ROW = RA * T + PAD;
+    extern __shared__ float2 sm[];
+
+    const int tid = threadIdx.x;
+    const int c = tid % T;
+    const int r = tid / T;
+    const int frame = blockIdx.y;
+    const int n2 = blockIdx.x * T + c;
+    const int N2 = p.N2;
+    const size_t M = (size_t)1 << p.log2M;
+    const size_t half = M >> 1;
+
+    const char *ring = reinterpret_cast<const char *>(p.ring);
+    const void *hopA = ring + (size_t)((p.hop0 + frame) % p.nhops) * p.hop_bytes;
+    const void *hopB = ring + (size_t)((p.hop0 + frame + 1) % p.nhops) * p.hop_bytes;
+
+    if (r < RB) {
+        float2 v[RA];
+        const int fmt = p.in_format;
+#pragma unroll
+        for (int j = 0; j < RA; j++) {
+            const size_t idx = (size_t)(r + RB * j) * N2 + n2;  // complex element within the frame
+            // first half of the frame (j < RA/2) comes from the older hop
+            float2 x = (j < RA / 2) ? load_sample(hopA, fmt, idx) : load_sample(hopB, fmt, idx - half);
+            if (p.is_real) {
+                float2 w = __ldg(reinterpret_cast<const float2 *>(p.window) + idx);
+                x.x *= w.x;
+                x.y *= w.y;
+            } else {
+                float w = __ldg(p.window + idx);
+                x.x *= w;
+                x.y *= w;
+            }
+            v[j] = x;
+        }
+        RegDft<RA>::run(v);
+#pragma unroll
+        for (int q = 0; q < RA; q++) {
+            float2 t = (q == 0) ? make_float2(1.f, 0.f) : __ldg(p.twA1 + q * RB + r);
+            sm[r * ROW + q * T + c] = (q == 0) ? v[q] : cmul(v[q], t);
+        }
+    }
+    __syncthreads();
+    if (r < RA) {
+        const int q = r;
+        float2 u[RB];
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) u[rr] = sm[rr * ROW + q * T + c];
+        RegDft<RB>::run(u);
+        float2 *Y = p.Y + (size_t)frame * M;
+        const int N1 = p.N1;
+#pragma unroll
+        for (int s = 0; s < RB; s++) {
+            const int k1 = q + RA * s;
+            int u1 = k1 - p.shift;
+            if (u1 < 0) u1 += N1;
+            // exponent of W_M: n2*k1, or the one-slot rotation N1*n2 for the IQ k1 = 0 row
+            const unsigned e = (p.shift && k1 == 0) ? (unsigned)N1 * (unsigned)n2 : (unsigned)n2 * (unsigned)k1;
+            const float2 tw = cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + (e >> 10)));
+            Y[(size_t)u1 * N2 + n2] = cmul(u[s], tw);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: grid (N1/T, frames), block T*max(RA,RB)
+// ------------------------------------------------------------------------------------------------
+template <int RA, int RB, int T>
+__global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const FwdParams p) {
+    constexpr int TPC = CMax<RA, RB>::v;
+    constexpr int ROW = RA * T + 1;  // odd stride: lanes along r hit distinct banks
+    extern __shared__ float2 sm[];
+
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.y;
+    const int N1 = p.N1, N2 = p.N2;
+    const size_t M = (size_t)1 << p.log2M;
+    const float2 *Y = p.Y + (size_t)frame * M;
+
+    {   // stage A: lanes along n2 (contiguous in Y)
+        const int r = tid % TPC;
+        const int c = tid / TPC;
+        if (r < RB) {
+            const float2 *src = Y + (size_t)(blockIdx.x * T + c) * N2;
+            float2 v[RA];
+#pragma unroll
+            for (int j = 0; j < RA; j++) v[j] = src[r + RB * j];
+            RegDft<RA>::run(v);
+#pragma unroll
+            for (int q = 0; q < RA; q++) {
+                float2 t = (q == 0) ? make_float2(1.f, 0.f) : __ldg(p.twA2 + q * RB + r);
+                sm[r * ROW + q * T + c] = (q == 0) ? v[q] : cmul(v[q], t);
+            }
+        }
+    }
+    __syncthreads();
+    {   // stage B: lanes along u1 (contiguous in the spectrum)
+        const int c = tid % T;
+        const int q = tid / T;
+        if (q < RA) {
+            float2 u[RB];
+#pragma unroll
+            for (int rr = 0; rr < RB; rr++) u[rr] = sm[rr * ROW + q * T + c];
+            RegDft<RB>::run(u);
+            float2 *out = p.out + (size_t)frame * p.out_stride;
+            const unsigned u1 = blockIdx.x * T + c;
+            const float scale = p.scale;
+#pragma unroll
+            for (int s = 0; s < RB; s++) {
+                const unsigned u2 = q + RA * s;
+                const size_t k = ((size_t)u1 + (size_t)N1 * u2 + p.shift) & (M - 1);
+                const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
+                out[k] = val;
+                if (k < (size_t)p.additional) out[M + k] = val;  // IQ wrap tail, src/fft.cpp:96-97
+                for (int pe = 0; pe < p.npeers; pe++) {
+                    float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
+                    po[k] = val;
+                    if (k < (size_t)p.additional) po[M + k] = val;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// waterfall quantiser - bit-exact restatement of vec_log2 / power_and_quantize (src/fft_impl.cpp:14-44).
+// Every float op is an explicit round-to-nearest intrinsic (no FMA contraction) in source order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vec_log2_dev(float val, int power_offset) {
+    unsigned bits = __float_as_uint(val);
+    float log_val = __fadd_rn((float)((int)((bits >> 23) & 0xFF) - 128), (float)power_offset);
+    bits &= ~(255u << 23);
+    bits += 127u << 23;
+    val = __uint_as_float(bits);
+    float poly = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(-0.34484843f, val), 2.02466578f), val), 0.67487759f);
+    return __fadd_rn(log_val, poly);
+}
+__device__ __forceinline__ int quantize_dev(float power, int power_offset) {
+    float v = __fadd_rn(__fmul_rn(__fmul_rn(vec_log2_dev(power, power_offset), 0.3010299956639812f), 20.f), 127.f);
+    v = (v > -128.f) ? v : -128.f;        // std::max(-128.f, v); NaN -> -128
+    int t = __float2int_rz(v);            // C truncation
+    return t & 0xFF;                      // int8 store keeps the low byte (wraps above 127 like x86)
+}
+
+struct PyrParams {
+    float2 *spec;            // spectrum (c2c: input, already normalised; r2c: OUTPUT written here)
+    size_t spec_stride;
+    const float2 *Z;         // r2c: packed half-size transform (unnormalised), [frames][M]
+    int8_t *quant;           // pyramid output [frames][pyr_stride]
+    size_t pyr_stride;
+    float *ptop;             // [frames][R/1024] level-10 power sums (only when levels > 11)
+    int log2R;               // display bins R = 1 << log2R
+    int levels;
+    int size_log2;           // round(log2(size)) + brightness_offset
+    int is_real;
+    float scale;             // r2c: 1/size
+    const float2 *TLr;       // r2c: W_size^j, j < 1024
+    const float2 *THr;       // r2c: W_size^(1024 j)
+    int npeers;
+    float2 *peers[kMaxPeers];
+};
+
+// grid (R/1024, frames), block 256: each thread owns 4 consecutive display bins.
+__global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+    __shared__ float warp_sum[8];
+    const int tid = threadIdx.x;
+    const int frame = blockIdx.y;
+    const size_t R = (size_t)1 << p.log2R;
+    const size_t d0 = (size_t)blockIdx.x * 1024 + 4 * tid;
+    float2 *spec = p.spec + (size_t)frame * p.spec_stride;
+    int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
+
+    float pw[4];
+    if (!p.is_real) {
+        // display bin d <-> FFT bin (d + R/2 + 1) mod R   (src/fft_impl.cpp:148-160)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const size_t k = (d0 + i + (R >> 1) + 1) & (R - 1);
+            const float2 x = spec[k];
+            pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+        }
+    } else {
+        // r2c split: X[k] = (Z[k] + conj(Z[M-k]))/2 - (i/2) W_size^k (Z[k] - conj(Z[M-k])), M = R
+        const float2 *Z = p.Z + (size_t)frame * R;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const size_t k = d0 + i;
+            const float2 a = Z[k];
+            const float2 b = Z[(R - k) & (R - 1)];
+            const float2 e = make_float2(a.x + b.x, a.y - b.y);
+            const float2 o = make_float2(a.x - b.x, a.y + b.y);
+            const float2 w = cmul(__ldg(p.TLr + (k & 1023)), __ldg(p.THr + (k >> 10)));
+            const float2 t = cmul(o, w);
+            float2 x = make_float2(0.5f * (e.x + t.y), 0.5f * (e.y - t.x));
+            if (k == 0) {
+                // Nyquist bin is left unnormalised by the reference (only outbuf_len = size/2 bins are
+                // divided, src/fft_impl.cpp:152-154)
+                const float2 ny = make_float2(a.x - a.y, 0.f);
+                spec[R] = ny;
+                for (int pe = 0; pe < p.npeers; pe++) (p.peers[pe] + (size_t)frame * p.spec_stride)[R] = ny;
+            }
+            x.x *= p.scale;
+            x.y *= p.scale;
+            spec[k] = x;
+            for (int pe = 0; pe < p.npeers; pe++) (p.peers[pe] + (size_t)frame * p.spec_stride)[k] = x;
+            pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+        }
+    }
+    const int L = p.levels;
+    const int off = p.size_log2;
+    // level 0
+    {
+        unsigned packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) packed |= (unsigned)quantize_dev(pw[i], off) << (8 * i);
+        *reinterpret_cast<unsigned *>(quant + d0) = packed;
+    }
+    size_t lvl_off = R;  // byte offset of level 1
+    if (L > 1) {
+        const float s0 = __fadd_rn(pw[0], pw[1]), s1 = __fadd_rn(pw[2], pw[3]);
+        const unsigned short pk = (unsigned short)(quantize_dev(s0, off - 1) | (quantize_dev(s1, off - 1) << 8));
+        *reinterpret_cast<unsigned short *>(quant + lvl_off + (d0 >> 1)) = pk;
+        lvl_off += R >> 1;
+        float s = __fadd_rn(s0, s1);
+        if (L > 2) {
+            quant[lvl_off + (d0 >> 2)] = (int8_t)quantize_dev(s, off - 2);
+            lvl_off += R >> 2;
+            // levels 3..7 inside the warp
+            const int lane = tid & 31;
+#pragma unroll
+            for (int lv = 3; lv <= 7; lv++) {
+                if (lv < L) {
+                    s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1 << (lv - 3)));
+                    if ((lane & ((1 << (lv - 2)) - 1)) == 0)
+                        quant[lvl_off + (d0 >> lv)] = (int8_t)quantize_dev(s, off - lv);
+                    lvl_off += R >> lv;
+                }
+            }
+            if (L > 8) {
+                if (lane == 0) warp_sum[tid >> 5] = s;
+                __syncthreads();
+                if (tid < 8) {
+                    float w = warp_sum[tid];
+                    const size_t b0 = (size_t)blockIdx.x * 1024;
+#pragma unroll
+                    for (int lv = 8; lv <= 10; lv++) {
+                        if (lv < L) {
+                            w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (lv - 8)));
+                            if ((tid & ((1 << (lv - 7)) - 1)) == 0)
+                                quant[lvl_off + ((b0 + 128 * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
+                            lvl_off += R >> lv;
+                        }
+                    }
+                    if (L > 11 && tid == 0) p.ptop[(size_t)frame * (R >> 10) + blockIdx.x] = w;
+                }
+            }
+        }
+    }
+}
+
+// levels 11.. (only for R > 2^20 or small waterfall_size): one block per frame, pairwise tree over
+// the level-10 sums left in ptop. Tiny.
+__global__ void pyramid_tail_kernel(const PyrParams p) {
+    const int frame = blockIdx.x;
+    const size_t R = (size_t)1 << p.log2R;
+    float *buf = p.ptop + (size_t)frame * (R >> 10);
+    int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
+    size_t lvl_off = 0;
+    for (int lv = 0; lv < 11; lv++) lvl_off += R >> lv;
+    size_t n = R >> 10;
+    for (int lv = 11; lv < p.levels; lv++) {
+        n >>= 1;
+        // in-place pairwise sum: element j <- buf[2j] + buf[2j+1]; done in two phases to avoid races
+        for (size_t base = 0; base < n; base += blockDim.x) {
+            size_t j = base + threadIdx.x;
+            float v = 0.f;
+            if (j < n) v = __fadd_rn(buf[2 * j], buf[2 * j + 1]);
+            __syncthreads();
+            if (j < n) {
+                buf[j] = v;
+                quant[lvl_off + j] = (int8_t)quantize_dev(v, p.size_log2 - lv);
+            }
+            __syncthreads();
+        }
+        lvl_off += R >> lv;
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,142 @@
+"""GPU parity: batched per-client demodulation through the C ABI vs the CPU oracle's restatement of
+AudioClient::send_audio (src/signal.cpp:102-298).
+
+Both sides consume the SAME spectrum (the engine's host mirror, wrap tail included), so the
+comparison isolates the client chain:
+  * slice offsets / placement / parity flip / overlap-add / demod: audio before DC removal within
+    1e-5 * max|y| per frame (north_star tolerance; FM compared as a wrapped angle);
+  * DC blocker + AGC + int16: BIT-EXACT when the oracle tails are fed the engine's own pre-DC audio
+    (strictly sequential float recurrences restated op-for-op), and within 1 LSB (rare 2) against
+    the full oracle chain;
+  * pwr within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from phantomsdr_b200 import SpectrumConfig, USB, LSB, AM, FM
+from phantomsdr_b200.synth import SignalSource, make_clients, ClientSpec
+from helpers import make_engine, make_oracle_fft, hop_as_floats
+
+pytestmark = pytest.mark.gpu
+
+
+class OracleTail:
+    def __init__(self, cfg):
+        self.dc = oracle.OracleDC(cfg.audio_sps // 750 * 2)
+        self.agc = oracle.OracleAGC(0.2, 50.0, 300.0, 200.0, float(cfg.audio_sps))
+
+    def run(self, pre):
+        y = self.agc.process(self.dc.remove(pre))
+        out = np.zeros(y.size, np.int32)
+        oracle.lib().orc_float_to_int16(y, out, 16384.0, y.size)
+        return out
+
+
+def run_case(cfg, clients, nframes, mode_changes=None, seed=7):
+    src = SignalSource(cfg, seed=seed)
+    eng = make_engine(cfg)
+    n = cfg.audio_fft_size
+    h = n // 2
+    nc = len(clients)
+    eng.clients_create(nc + 3, n, cfg.audio_sps)  # a few spare, closed slots
+    orcs, tails = [], []
+    for i, c in enumerate(clients):
+        eng.client_open(i, c.l, c.mid, c.r, c.mode)
+        o = oracle.OracleClient(cfg.is_real, n, cfg.audio_sps, cfg.fft_result_size)
+        assert o.on_window_message(c.l, c.mid, c.r)
+        o.set_audio_demodulation(c.mode)
+        orcs.append(o)
+        tails.append(OracleTail(cfg))
+    ring = [eng.malloc(cfg.hop_floats) for _ in range(3)]
+    ring[0][:] = hop_as_floats(src.next_hop())
+    ring[1][:] = hop_as_floats(src.next_hop())
+    idx = 0
+    stats = {"pre_rel": 0.0, "pcm_max": 0, "pcm_diff_frac": 0.0}
+    total = diff = 0
+    for frame in range(nframes):
+        if mode_changes and frame in mode_changes:
+            for (ci, mode) in mode_changes[frame]:
+                eng.client_set_demodulation(ci, mode)
+                orcs[ci].on_demodulation_message(mode)
+                tails[ci].agc.reset()
+                clients[ci] = ClientSpec(clients[ci].l, clients[ci].mid, clients[ci].r, mode)
+        a1, a2 = ring[idx], ring[(idx + 1) % 3]
+        (eng.load_real_input if cfg.is_real else eng.load_complex_input)(a1, a2)
+        ring[(idx + 2) % 3][:] = hop_as_floats(src.next_hop())
+        idx = (idx + 1) % 3
+        eng.execute()
+        spec = eng.get_output_buffer().view(np.complex64).copy()
+        pcm, pwr, valid = eng.clients_execute(frame)
+        pre = eng.clients_read_pre_dc()
+        assert not valid[nc:].any(), "closed slots must read back invalid"
+        for i, (c, o) in enumerate(zip(clients, orcs)):
+            ok, pcm_ref, pwr_ref, pre_ref = o.send_audio(spec, cfg.fft_size, frame)
+            assert ok and valid[i] == 1
+            scale = max(float(np.abs(pre_ref).max()), 1e-30)
+            if c.mode == FM:
+                d = np.angle(np.exp(1j * (pre[i].astype(np.float64) - pre_ref)))
+                assert (np.abs(d) > 1e-3).mean() <= 0.01, f"client {i} FM: angle error"
+            else:
+                err = float(np.abs(pre[i] - pre_ref).max()) / scale
+                stats["pre_rel"] = max(stats["pre_rel"], err)
+                assert err <= 1e-5, f"frame {frame} client {i} mode {c.mode}: pre-DC audio rel err {err:.2e}"
+            assert abs(pwr[i] - pwr_ref) <= 1e-5 * max(pwr_ref, 1e-30), f"client {i}: pwr {pwr[i]} vs {pwr_ref}"
+            # sequential tails: bit-exact on identical input
+            exact = tails[i].run(pre[i])
+            assert np.array_equal(pcm[i], exact), f"frame {frame} client {i}: DC/AGC/int16 tail not bit-exact"
+            if c.mode != FM:
+                dd = np.abs(pcm[i] - pcm_ref)
+                stats["pcm_max"] = max(stats["pcm_max"], int(dd.max()))
+                total += dd.size
+                diff += int((dd != 0).sum())
+    stats["pcm_diff_frac"] = diff / max(total, 1)
+    eng.close()
+    return stats
+
+
+def cfg_for_n(fft_size, n_target, is_real=False, audio_sps=12000):
+    # pick sps so that audio_fft_size == n_target (src/spectrumserver.cpp:151)
+    sps = int(audio_sps * fft_size / (n_target - 1.5))
+    cfg = SpectrumConfig(sps=sps, fft_size=fft_size, is_real=is_real, audio_sps=audio_sps)
+    assert cfg.audio_fft_size == n_target, cfg.audio_fft_size
+    return cfg
+
+
+@pytest.mark.parametrize("n_target,fft_size,is_real", [
+    (360, 1 << 17, False),   # cfg 2's audio size: 2^3 * 3^2 * 5
+    (548, 1 << 17, False),   # cfg 1 at 2.88 MSPS: 4 * 137 (generic prime radix)
+    (492, 1 << 16, False),   # cfg 1 at 3.2 MSPS: 4 * 3 * 41
+    (360, 1 << 18, True),    # real input: base_idx 0, opposite parity rule
+])
+def test_clients_all_modes(gpu_required, n_target, fft_size, is_real):
+    cfg = cfg_for_n(fft_size, n_target, is_real)
+    src = SignalSource(cfg, seed=7)
+    tones = [src.display_bin(t) for t in src.tones]
+    clients = make_clients(cfg, 24, modes=(USB, LSB, AM, FM), tones=tones, on_tone_fraction=0.7)
+    stats = run_case(cfg, clients, nframes=18)
+    assert stats["pcm_max"] <= 2 and stats["pcm_diff_frac"] <= 0.02, stats
+
+
+def test_clients_edges_and_mode_switch(gpu_required):
+    """Edge slices: l near 0 (IQ wrap through the tail), r-l = n (max), r = l (empty), odd/even
+    floor(mid) for both frame parities, slice not containing mid, demodulation switches with AGC
+    reset (src/signal.cpp:316-328)."""
+    cfg = cfg_for_n(1 << 17, 360)
+    R, n = cfg.fft_result_size, cfg.audio_fft_size
+    half_wrap = R - (cfg.fft_size // 2 + 1)  # display l whose slice starts at FFT bin R-1 ... wraps into the tail
+    clients = [
+        ClientSpec(half_wrap - 40, half_wrap + 10.25, half_wrap - 40 + n, USB),
+        ClientSpec(half_wrap - 3, half_wrap + 100.5, half_wrap + 200, AM),
+        ClientSpec(0, 0.0, 90, USB),
+        ClientSpec(0, 45.5, 90, LSB),
+        ClientSpec(1000, 1001.0, 1000, USB),          # empty slice
+        ClientSpec(2000, 2150.75, 2300, FM),
+        ClientSpec(3001, 3001.5, 3091, USB),          # odd floor(mid)
+        ClientSpec(3000, 3000.5, 3090, USB),          # even floor(mid)
+        ClientSpec(5000, 5400.0, 5100, USB),          # mid outside the slice
+        ClientSpec(R - 1 - n, R - 200.0, R - 1, LSB), # top edge
+    ]
+    changes = {5: [(0, LSB), (5, AM)], 9: [(0, AM), (1, FM), (5, USB)], 12: [(0, USB)]}
+    stats = run_case(cfg, clients, nframes=16, mode_changes=changes)
+    assert stats["pcm_max"] <= 2, stats
