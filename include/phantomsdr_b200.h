@@ -111,6 +111,7 @@ int b200_execute(b200_engine *e);
 #define B200_OPT_RELOAD_BOTH 1   /* 0 (default) / 1 */
 #define B200_OPT_HOST_MIRROR 2   /* bitmask: 1 = spectrum, 2 = pyramid; default 3 */
 #define B200_OPT_INPUT_FORMAT 3  /* B200_FMT_*: format of the halves given to b200_load_raw_input */
+#define B200_OPT_STAGE_MASK 4    /* profiling aid: bit0 = FFT pass 1, bit1 = pass 2, bit2 = pyramid; default 7 */
 int b200_set_option(b200_engine *e, int option, int value);
 
 /* SURVEY 8f N1 - SampleConverter<T>::read fused into the first FFT pass: halves are raw
@@ -146,6 +147,9 @@ size_t b200_pyramid_stride(b200_engine *e);
 int b200_sync(b200_engine *e);
 /* The engine's cudaStream_t (as void*), so callers can order their own work / events on it. */
 void *b200_stream(b200_engine *e);
+/* Run on the caller's stream instead (e.g. the framework's current stream); NULL restores the
+ * engine's own. The engine synchronises its previous stream first. */
+int b200_set_stream(b200_engine *e, void *cuda_stream);
 /* Adopt `dev_ptr` (device memory of b200_spectrum_bins() float2) as the spectrum buffer the client
  * kernels read - used on non-ingest ranks, where the frame arrives by NCCL broadcast / peer store.
  * Pass NULL to go back to the engine-owned buffer. */

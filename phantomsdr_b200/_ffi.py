@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200_pyramid_stride": (_sz, [_vp]),
     "b200_sync": (_i, [_vp]),
     "b200_stream": (_vp, [_vp]),
+    "b200_set_stream": (_i, [_vp, _vp]),
     "b200_bind_spectrum": (_i, [_vp, _vp]),
     "b200_set_peer_spectra": (_i, [_vp, _i, _pp]),
     "b200_ipc_export": (_i, [_vp, _vp, _vp]),

@@ -20,7 +20,7 @@ from ._ffi import B200Error, check  # noqa: F401
 
 FORWARD, BACKWARD = 0, 1
 FMT_F32, FMT_U8, FMT_S8, FMT_U16, FMT_S16 = 0, 1, 2, 3, 4
-OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT = 1, 2, 3
+OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_STAGE_MASK = 1, 2, 3, 4
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 
@@ -178,6 +178,10 @@ class B200FFT:
     @property
     def stream(self) -> int:
         return self.L.b200_stream(self.h) or 0
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """Enqueue on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own."""
+        check(self.L.b200_set_stream(self.h, cuda_stream or None))
 
     def bind_spectrum(self, dev_ptr: int) -> None:
         check(self.L.b200_bind_spectrum(self.h, dev_ptr))

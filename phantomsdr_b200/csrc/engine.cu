@@ -92,7 +92,8 @@ struct b200_engine {
     int log2M = 0;
     size_t R = 0;  // fft_result_size
     SubPlan sp1{}, sp2{};
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream work is enqueued on
+    cudaStream_t own_stream = nullptr;  // created by the engine
 
     float *d_window = nullptr;
     float2 *d_Y = nullptr, *d_Z = nullptr, *d_spec = nullptr, *spec_bound = nullptr;
@@ -116,6 +117,7 @@ struct b200_engine {
     long frame_hop0 = -1;
     int opt_reload_both = 0;
     int opt_mirror = 3;
+    int opt_stage_mask = 7;
 
     int npeers = 0;
     float2 *peers[kMaxPeers] = {};
@@ -231,10 +233,12 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         p.additional = 0;
         p.npeers = 0;
     }
-    int rc = dispatch_pass1(e, p, frames);
+    int rc = 0;
+    if (e->opt_stage_mask & 1) rc = dispatch_pass1(e, p, frames);
     if (rc) return rc;
-    rc = dispatch_pass2(e, p, frames);
+    if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames);
     if (rc) return rc;
+    if (!(e->opt_stage_mask & 4)) return 0;
 
     PyrParams q{};
     q.spec = spec;
@@ -501,7 +505,8 @@ int b200_engine_create(b200_engine **out, size_t size, int nthreads, int downsam
     e->size = size;
     e->levels = downsample_levels;
     e->size_log2 = (int)round(log2((double)size)) + brightness_offset;  // src/fft_impl.cpp:68
-    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    cudaError_t err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+    e->stream = e->own_stream;
     if (err != cudaSuccess) {
         delete e;
         return fail(B200_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(err));
@@ -534,7 +539,7 @@ void b200_engine_destroy(b200_engine *e) {
         if (p) cudaFree(p);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_quant) cudaFreeHost(e->h_quant);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
 
@@ -614,6 +619,7 @@ int b200_set_option(b200_engine *e, int option, int value) {
     switch (option) {
     case B200_OPT_RELOAD_BOTH: e->opt_reload_both = value ? 1 : 0; return 0;
     case B200_OPT_HOST_MIRROR: e->opt_mirror = value & 3; return 0;
+    case B200_OPT_STAGE_MASK: e->opt_stage_mask = value & 7; return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
         if (value != e->in_format) {
@@ -689,6 +695,13 @@ int b200_sync(b200_engine *e) {
     return 0;
 }
 void *b200_stream(b200_engine *e) { return e ? (void *)e->stream : nullptr; }
+int b200_set_stream(b200_engine *e, void *cuda_stream) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+    return 0;
+}
 
 int b200_bind_spectrum(b200_engine *e, void *dev_ptr) {
     if (!e) return fail(B200_EINVAL, "null engine");
