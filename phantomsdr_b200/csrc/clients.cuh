@@ -77,11 +77,13 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// One Stockham stage of radix R (sign +1):  x[t + j*items] -> y[q + s*(R*p + r)], t = p*s + q
+// One Stockham stage of radix R (sign +1):  x[t + j*items] -> y[q + s*(R*p + r)], t = p*s + q.
+// The whole CTA (nthr threads) shares the work.
 template <int R>
-__device__ __forceinline__ void ifft_stage_fixed(const float2 *x, float2 *y, int n, int s, const float2 *Wn, int lane) {
+__device__ __forceinline__ void ifft_stage_fixed(const float2 *x, float2 *y, int n, int s, const float2 *Wn, int tid,
+                                                 int nthr) {
     const int items = n / R;
-    for (int t = lane; t < items; t += 32) {
+    for (int t = tid; t < items; t += nthr) {
         const int p = t / s, q = t - p * s;
         float2 a[R];
 #pragma unroll
@@ -130,12 +132,12 @@ __device__ __forceinline__ void ifft_stage_fixed(const float2 *x, float2 *y, int
     }
 }
 
-// generic (prime) radix: one lane per OUTPUT, R complex MACs each
+// generic (prime) radix: one thread per OUTPUT, R complex MACs each
 __device__ __forceinline__ void ifft_stage_generic(const float2 *x, float2 *y, int n, int s, int R, const float2 *Wn,
-                                                   int lane) {
+                                                   int tid, int nthr) {
     const int items = n / R;
     const int step = n / R;  // W_R = Wn[n/R]
-    for (int o = lane; o < n; o += 32) {
+    for (int o = tid; o < n; o += nthr) {
         const int t = o / R, r = o - t * R;
         const int p = t / s, q = t - p * s;
         float2 acc = x[t];
@@ -153,16 +155,16 @@ __device__ __forceinline__ void ifft_stage_generic(const float2 *x, float2 *y, i
     }
 }
 
-// grid: ceil(nactive / WPB) blocks of WPB warps; dynamic smem WPB * 2n float2
-template <int WPB>
-__global__ void __launch_bounds__(WPB * 32) client_demod_kernel(const ClientArrays ca, const ClientLaunch cl) {
+// grid: one CTA per active client, TPB threads; dynamic smem 2n float2
+template <int TPB>
+__global__ void __launch_bounds__(TPB) client_demod_kernel(const ClientArrays ca, const ClientLaunch cl) {
     extern __shared__ float2 smem_c[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = blockIdx.x * WPB + warp;
-    if (ci >= cl.nactive) return;
+    __shared__ float s_red[TPB / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ci = blockIdx.x;
     const int slot = cl.order[ci];
     const int n = ca.n, h = ca.h;
-    float2 *bufX = smem_c + (size_t)warp * 2 * n;
+    float2 *bufX = smem_c;
     float2 *bufY = bufX + n;
     const ClientSlot cs = ca.slots[slot];
     const size_t R = cl.is_real ? cl.fft_size / 2 : cl.fft_size;
@@ -177,26 +179,26 @@ __global__ void __launch_bounds__(WPB * 32) client_demod_kernel(const ClientArra
     float2 *bb_hi = ca.bb_hi + (size_t)slot * h;
 
     if (cs.flags & CF_RESET_ALL) {  // freshly opened slot: zeroed scratch as AudioClient's ctor (signal.cpp:38-52)
-        for (int i = lane; i < h; i += 32) {
+        for (int i = tid; i < h; i += TPB) {
             real_prev[i] = 0.f;
             real_hi[i] = 0.f;
             bb_hi[i] = make_float2(0.f, 0.f);
         }
-        if (lane == 0) {
+        if (tid == 0) {
             ca.bb_last[slot] = make_float2(0.f, 0.f);
             ca.hi_diverged[slot] = 0;
         }
-        __syncwarp();
+        __syncthreads();
     }
 
     for (int f = 0; f < cl.nframes; f++) {
         const unsigned long long frame_num = cl.frame_num0 + f;
         const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
-        for (int i = lane; i < n; i += 32) bufX[i] = make_float2(0.f, 0.f);
-        __syncwarp();
+        for (int i = tid; i < n; i += TPB) bufX[i] = make_float2(0.f, 0.f);
+        __syncthreads();
         // gather + placement + slice power (signal.cpp:117-198)
         float pw = 0.f;
-        for (int i = lane; i < len; i += 32) {
+        for (int i = tid; i < len; i += TPB) {
             const float2 v = buf[i];
             pw += v.x * v.x + v.y * v.y;
             if (mode == MODE_USB || mode == MODE_LSB) {
@@ -216,55 +218,55 @@ __global__ void __launch_bounds__(WPB * 32) client_demod_kernel(const ClientArra
             }
         }
         pw = warp_sum(pw);
-        __syncwarp();
+        if (lane == 0) s_red[warp] = pw;
+        __syncthreads();
         // inverse FFT, unnormalised (signal.cpp:138,154,214)
         float2 *x = bufX, *y = bufY;
         int s = 1;
         for (int st = 0; st < ca.nstages; st++) {
             const int Rr = ca.radix[st];
-            if (Rr == 4) ifft_stage_fixed<4>(x, y, n, s, ca.Wn, lane);
-            else if (Rr == 2) ifft_stage_fixed<2>(x, y, n, s, ca.Wn, lane);
-            else if (Rr == 3) ifft_stage_fixed<3>(x, y, n, s, ca.Wn, lane);
-            else if (Rr == 5) ifft_stage_fixed<5>(x, y, n, s, ca.Wn, lane);
-            else ifft_stage_generic(x, y, n, s, Rr, ca.Wn, lane);
+            if (Rr == 4) ifft_stage_fixed<4>(x, y, n, s, ca.Wn, tid, TPB);
+            else if (Rr == 2) ifft_stage_fixed<2>(x, y, n, s, ca.Wn, tid, TPB);
+            else if (Rr == 3) ifft_stage_fixed<3>(x, y, n, s, ca.Wn, tid, TPB);
+            else if (Rr == 5) ifft_stage_fixed<5>(x, y, n, s, ca.Wn, tid, TPB);
+            else ifft_stage_generic(x, y, n, s, Rr, ca.Wn, tid, TPB);
             s *= Rr;
             float2 *t = x;
             x = y;
             y = t;
-            __syncwarp();
+            __syncthreads();
         }
         // x holds the time-domain result
         const int m_idx = cs.m_floor;
         const bool negate = (frame_num & 1ull) && (((m_idx % 2 == 0) && !cl.is_real) || ((m_idx % 2 == 1) && cl.is_real));
         const float sg = negate ? -1.f : 1.f;
         float *audio = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
-        bool nan_seen = false;
+        int nan_seen = 0;
         if (mode == MODE_USB || mode == MODE_LSB) {
             // signal.cpp:155-172: (LSB: time reverse), parity negate, overlap-add
-            for (int t = lane; t < h; t += 32) {
+            for (int t = tid; t < h; t += TPB) {
                 const float lo = (mode == MODE_USB) ? x[t].x : x[n - 1 - t].x;
                 const float o = __fadd_rn(sg * lo, real_prev[t]);
                 nan_seen |= (o != o);
                 audio[t] = o;
             }
-            nan_seen = __any_sync(0xffffffffu, nan_seen);
+            nan_seen = __syncthreads_or(nan_seen);
             float *dst = nan_seen ? real_hi : real_prev;  // signal.cpp:266-275: prev only advances on a sent frame
-            __syncwarp();
-            for (int t = lane; t < h; t += 32) {
+            for (int t = tid; t < h; t += TPB) {
                 const float hi = (mode == MODE_USB) ? x[h + t].x : x[n - 1 - (h + t)].x;
                 dst[t] = sg * hi;
             }
-            if (lane == 0) ca.hi_diverged[slot] = nan_seen ? 1 : 0;
+            if (tid == 0) ca.hi_diverged[slot] = nan_seen ? 1 : 0;
         } else {
             // signal.cpp:200-263
             const float2 prev_last = ca.bb_last[slot];
             float2 *bb = y;  // assemble the overlapped first half in the free buffer
-            for (int t = lane; t < h; t += 32) {
+            for (int t = tid; t < h; t += TPB) {
                 const float2 lo = x[t], old = bb_hi[t];
                 bb[t] = make_float2(__fadd_rn(sg * lo.x, old.x), __fadd_rn(sg * lo.y, old.y));
             }
-            __syncwarp();
-            for (int t = lane; t < h; t += 32) {
+            __syncthreads();
+            for (int t = tid; t < h; t += TPB) {
                 const float2 hi = x[h + t];
                 bb_hi[t] = make_float2(sg * hi.x, sg * hi.y);
                 const float2 b = bb[t];
@@ -281,49 +283,91 @@ __global__ void __launch_bounds__(WPB * 32) client_demod_kernel(const ClientArra
                 nan_seen |= (o != o);
                 audio[t] = o;
             }
-            nan_seen = __any_sync(0xffffffffu, nan_seen);
-            if (lane == 0) ca.bb_last[slot] = bb[h - 1];
+            nan_seen = __syncthreads_or(nan_seen);
+            if (tid == 0) ca.bb_last[slot] = bb[h - 1];
             if (!nan_seen && ca.hi_diverged[slot]) {
                 // audio_real_prev <- audio_real[n/2..n) left behind by a NaN-dropped SSB frame
-                for (int t = lane; t < h; t += 32) real_prev[t] = real_hi[t];
-                __syncwarp();
-                if (lane == 0) ca.hi_diverged[slot] = 0;
+                for (int t = tid; t < h; t += TPB) real_prev[t] = real_hi[t];
+                __syncthreads();
+                if (tid == 0) ca.hi_diverged[slot] = 0;
             }
         }
-        if (lane == 0) {
+        if (tid == 0) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < TPB / 32; w++) tot += s_red[w];
             ca.valid_a[(size_t)f * ca.max_clients + slot] = nan_seen ? 0 : 1;
-            ca.pwr[(size_t)f * ca.max_clients + slot] = pw;
+            ca.pwr[(size_t)f * ca.max_clients + slot] = tot;
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sequential tails, one lane per client, 32 clients per block (8 warps help with tile movement).
+// Sequential tails. The float recurrences (two running sums of the DC blocker, the AGC gain) are
+// strictly serial per client, so they run one LANE per client (cpb clients per block) and are
+// stripped to the loop-carried adds; everything that is not loop-carried (divisions, window
+// maxima, conversions) runs beside them with lanes along the sample index.
+// Tiles are [j][client] with pitch cpb + 1 (odd): conflict-free for lanes along j and along client.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTailThreads = 256;
-// tiles are [j][client] with pitch cpb + 1 (odd): conflict-free for lanes along j and lanes along client
+constexpr int kTailThreads = 512;
+constexpr int kTailWarps = kTailThreads / 32;
+constexpr int kTailMaxCpb = 16;  // one warp per client in the parallel phases
 
-__device__ __forceinline__ int floordiv(long long a, int b) {
+__device__ __forceinline__ long long floordiv_ll(long long a, int b) {
     long long q = a / b;
     if ((a % b != 0) && ((a < 0) != (b < 0))) q--;
-    return (int)q;
+    return q;
 }
 
+// running sum  s <- (s - old) + x  over j = 0..h-1 for one client column `ci` (lane = client), written to out.
+// old_j = state[j] for j < D, in[j - D] afterwards. Loads are grouped four iterations ahead of the two
+// dependent adds so only the adds sit on the loop-carried path.
+__device__ __forceinline__ float running_sum_serial(float s, const float *state, const float *in, float *out, int h,
+                                                    int D, int P, int ci) {
+    int j = 0;
+    for (; j + 4 <= h; j += 4) {
+        float o[4], x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int jj = j + u;
+            o[u] = (jj < D) ? state[jj * P + ci] : in[(jj - D) * P + ci];
+            x[u] = in[jj * P + ci];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            s = __fadd_rn(__fadd_rn(s, -o[u]), x[u]);
+            o[u] = s;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) out[(j + u) * P + ci] = o[u];
+    }
+    for (; j < h; j++) {
+        const float o = (j < D) ? state[j * P + ci] : in[(j - D) * P + ci];
+        s = __fadd_rn(__fadd_rn(s, -o), in[j * P + ci]);
+        out[j * P + ci] = s;
+    }
+    return s;
+}
+
+// KB = ceil(h / 32) when known at compile time (all row loads of a client are issued before any is
+// consumed), 0 = runtime loops for unusually long audio frames.
+template <int KB>
 __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientArrays ca, const ClientLaunch cl) {
     extern __shared__ float smem_t[];
     const int h = ca.h, D = ca.D, L = ca.L, NC = ca.NC;
-    const int cpb = cl.cpb, kPitch = cl.cpb + 1;
-    float *tA = smem_t;                 // [h][33]  audio in, later AGC output
-    float *tM = tA + h * kPitch;        // [h][33]  first-stage moving averages
-    float *tY = tM + h * kPitch;        // [h][33]  DC blocker output
-    float *tO = tY + h * kPitch;        // [2h][33] the two oldest AGC chunks touching the window
-    float *tS = tO + 2 * h * kPitch;    // [2h][33] suffix maxima of |tO| within each chunk
-    float *tDx = tS + 2 * h * kPitch;   // [D][33]
-    float *tDm = tDx + D * kPitch;      // [D][33]
+    const int cpb = cl.cpb, P = cl.cpb + 1;
+    float *tA = smem_t;           // [h][P] audio in (DC input)
+    float *tM = tA + h * P;       // [h][P] running sum 1 -> first-stage average
+    float *tY = tM + h * P;       // [h][P] running sum 2 -> DC blocker output
+    float *tC = tY + h * P;       // [h][P] look-ahead-delayed sample -> AGC output
+    float *tP = tC + h * P;       // [h][P] window maximum over the old samples -> desired gain
+    float *tDx = tP + h * P;      // [D][P]
+    float *tDm = tDx + D * P;     // [D][P]
     __shared__ int s_slot[32];
-    __shared__ int s_ca[32];
     __shared__ unsigned char s_valid[32];
+    __shared__ long long s_t0[32];
+    __shared__ float s_pmax[32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g0 = blockIdx.x * cpb;
@@ -334,130 +378,230 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
     float sum1 = 0.f, sum2 = 0.f, gain = 0.f;
     long long t0 = 0;
     const int my_slot = s_slot[lane];
-    if (warp == 0 && my_slot >= 0) {
-        const int fl = ca.slots[my_slot].flags;
-        if (fl & (CF_RESET_ALL | CF_RESET_AGC)) {  // AGC::reset, audioprocessing.cpp:70-74
-            float *ring = ca.agc_ring + (size_t)my_slot * NC * h;
-            for (int i = 0; i < NC * h; i++) ring[i] = 0.f;
-            for (int i = 0; i < NC; i++) ca.agc_cmax[(size_t)my_slot * NC + i] = 0.f;
-            gain = 0.f;
-            t0 = 0;
-        } else {
-            gain = ca.agc_gain[my_slot];
-            t0 = ca.agc_t0[my_slot];
-        }
-        if (fl & CF_RESET_ALL) {
-            for (int i = 0; i < D; i++) {
-                ca.dc_x[(size_t)my_slot * D + i] = 0.f;
-                ca.dc_m[(size_t)my_slot * D + i] = 0.f;
+    {
+        // resets (AGC::reset, audioprocessing.cpp:70-74; fresh slot): lanes along the arrays
+        for (int ci = warp; ci < cpb; ci += kTailWarps) {
+            const int slot = s_slot[ci];
+            if (slot < 0) continue;
+            const int fl = ca.slots[slot].flags;
+            if (fl & (CF_RESET_ALL | CF_RESET_AGC)) {
+                float *ring = ca.agc_ring + (size_t)slot * NC * h;
+                for (int i = lane; i < NC * h; i += 32) ring[i] = 0.f;
+                for (int i = lane; i < NC; i += 32) ca.agc_cmax[(size_t)slot * NC + i] = 0.f;
             }
-            sum1 = sum2 = 0.f;
-        } else {
-            sum1 = ca.dc_sum[2 * my_slot];
-            sum2 = ca.dc_sum[2 * my_slot + 1];
+            if (fl & CF_RESET_ALL)
+                for (int i = lane; i < D; i += 32) {
+                    ca.dc_x[(size_t)slot * D + i] = 0.f;
+                    ca.dc_m[(size_t)slot * D + i] = 0.f;
+                }
+        }
+        if (warp == 0 && my_slot >= 0) {
+            const int fl = ca.slots[my_slot].flags;
+            if (!(fl & (CF_RESET_ALL | CF_RESET_AGC))) {
+                gain = ca.agc_gain[my_slot];
+                t0 = ca.agc_t0[my_slot];
+            }
+            if (!(fl & CF_RESET_ALL)) {
+                sum1 = ca.dc_sum[2 * my_slot];
+                sum2 = ca.dc_sum[2 * my_slot + 1];
+            }
         }
     }
     __syncthreads();
 
+    const float Df = (float)D;
+    const int nb = (KB > 0) ? KB : (h + 31) / 32;
     for (int f = 0; f < cl.nframes; f++) {
         if (warp == 0) {
-            int v = 0, cidx = 0;
-            if (my_slot >= 0) {
-                v = ca.valid_a[(size_t)f * ca.max_clients + my_slot];
-                cidx = floordiv(t0 - L + 1, h);
-            }
-            s_valid[lane] = (unsigned char)v;
-            s_ca[lane] = cidx;
+            s_valid[lane] = (my_slot >= 0) ? ca.valid_a[(size_t)f * ca.max_clients + my_slot] : 0;
+            s_t0[lane] = t0;
         }
         __syncthreads();
-        // ---- tile loads (lanes along j: coalesced) ----
-        for (int ci = warp; ci < cpb; ci += kTailThreads / 32) {
+        // ---- P0: loads, lanes along j. Old-sample window maxima and delayed samples. ----
+        for (int ci = warp; ci < cpb; ci += kTailWarps) {
             const int slot = s_slot[ci];
             if (slot < 0 || !s_valid[ci]) continue;
             const float *a = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
-            for (int j = lane; j < h; j += 32) tA[j * kPitch + ci] = a[j];
-            for (int j = lane; j < D; j += 32) {
-                tDx[j * kPitch + ci] = ca.dc_x[(size_t)slot * D + j];
-                tDm[j * kPitch + ci] = ca.dc_m[(size_t)slot * D + j];
-            }
-            const int c0 = s_ca[ci];
+            // AGC window of output j is samples [t0+j-L+1, t0+j]. Its old part starts at chunk c0,
+            // column col0 and, as j grows, walks through chunk c0 then chunk c0+1.
+            const long long tt = s_t0[ci];
+            const long long lo0 = tt - L + 1;
+            const long long c0 = floordiv_ll(lo0, h);
+            const int col0 = (int)(lo0 - c0 * h);
+            const long long Fc = tt / h;  // chunk index of the samples produced by this frame
             const float *ring = ca.agc_ring + (size_t)slot * NC * h;
-            for (int rr = 0; rr < 2; rr++) {
-                const int row = (((c0 + rr) % NC) + NC) % NC;
-                const float *src = ring + (size_t)row * h;
-                // suffix max of |x| inside the chunk, 32 at a time from the end
-                float carry = 0.f;
-                for (int base = ((h - 1) / 32) * 32; base >= 0; base -= 32) {
-                    const int j = base + lane;
-                    const float xv = (j < h) ? src[j] : 0.f;
-                    float m = fabsf(xv);
+            const float *cmax = ca.agc_cmax + (size_t)slot * NC;
+            const float *row0 = ring + (size_t)((((c0) % NC) + NC) % NC) * h;
+            const float *row1 = ring + (size_t)((((c0 + 1) % NC) + NC) % NC) * h;
+            // maxima of the whole chunks strictly between the walking chunk and this frame
+            float m0 = 0.f, m1 = 0.f;
+            for (long long c = c0 + 1 + lane; c <= Fc - 1; c += 32) {
+                const float v = cmax[(int)(((c % NC) + NC) % NC)];
+                m0 = fmaxf(m0, v);
+                if (c >= c0 + 2) m1 = fmaxf(m1, v);
+            }
+            if constexpr (KB > 0) {
+                float ra[KB], r0[KB], r1[KB];
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const float other = __shfl_down_sync(0xffffffffu, m, o);
-                        if (lane + o < 32) m = fmaxf(m, other);
+                for (int b = 0; b < KB; b++) {  // every global load of this client is in flight together
+                    const int col = 32 * b + lane;
+                    ra[b] = (col < h) ? a[col] : 0.f;
+                    r0[b] = (col < h) ? row0[col] : 0.f;
+                    r1[b] = (col < h) ? row1[col] : 0.f;
+                }
+                for (int j = lane; j < D; j += 32) {
+                    tDx[j * P + ci] = ca.dc_x[(size_t)slot * D + j];
+                    tDm[j * P + ci] = ca.dc_m[(size_t)slot * D + j];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+                }
+#pragma unroll
+                for (int b = 0; b < KB; b++) {
+                    const int col = 32 * b + lane;
+                    if (col < h) tA[col * P + ci] = ra[b];
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const float mfull = rr ? m1 : m0;
+                    float carry = 0.f;
+#pragma unroll
+                    for (int b = KB - 1; b >= 0; b--) {  // suffix max of |x| inside the chunk, from the end
+                        const int col = 32 * b + lane;
+                        const float xv = rr ? r1[b] : r0[b];
+                        float m = fabsf(xv);
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const float other = __shfl_down_sync(0xffffffffu, m, o);
+                            if (lane + o < 32) m = fmaxf(m, other);
+                        }
+                        m = fmaxf(m, carry);
+                        const int j = rr * h + col - col0;  // output index served by (rr, col)
+                        if (col < h && j >= 0 && j < h) {
+                            tC[j * P + ci] = xv;
+                            tP[j * P + ci] = fmaxf(m, mfull);
+                        }
+                        carry = __shfl_sync(0xffffffffu, m, 0);
                     }
-                    m = fmaxf(m, carry);
-                    if (j < h) {
-                        tO[(rr * h + j) * kPitch + ci] = xv;
-                        tS[(rr * h + j) * kPitch + ci] = m;
+                }
+            } else {
+                for (int j = lane; j < h; j += 32) tA[j * P + ci] = a[j];
+                for (int j = lane; j < D; j += 32) {
+                    tDx[j * P + ci] = ca.dc_x[(size_t)slot * D + j];
+                    tDm[j * P + ci] = ca.dc_m[(size_t)slot * D + j];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+                }
+                for (int rr = 0; rr < 2; rr++) {
+                    const float *src = rr ? row1 : row0;
+                    const float mfull = rr ? m1 : m0;
+                    float carry = 0.f;
+                    for (int b = nb - 1; b >= 0; b--) {
+                        const int col = 32 * b + lane;
+                        const float xv = (col < h) ? src[col] : 0.f;
+                        float m = fabsf(xv);
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const float other = __shfl_down_sync(0xffffffffu, m, o);
+                            if (lane + o < 32) m = fmaxf(m, other);
+                        }
+                        m = fmaxf(m, carry);
+                        const int j = rr * h + col - col0;
+                        if (col < h && j >= 0 && j < h) {
+                            tC[j * P + ci] = xv;
+                            tP[j * P + ci] = fmaxf(m, mfull);
+                        }
+                        carry = __shfl_sync(0xffffffffu, m, 0);
                     }
-                    carry = __shfl_sync(0xffffffffu, m, 0);
                 }
             }
         }
         __syncthreads();
-        // ---- sequential chains, lane = client ----
+        // ---- P1 (serial): first running sum of the DC blocker, src/utils.h:80-85 ----
+        if (warp == 0 && my_slot >= 0 && s_valid[lane]) sum1 = running_sum_serial(sum1, tDx, tA, tM, h, D, P, lane);
+        __syncthreads();
+        // ---- P2 (parallel): getAverage() = sum / length ----
+        for (int ci = warp; ci < cpb; ci += kTailWarps) {
+            if (s_slot[ci] < 0 || !s_valid[ci]) continue;
+            for (int j = lane; j < h; j += 32) tM[j * P + ci] = __fdiv_rn(tM[j * P + ci], Df);
+        }
+        __syncthreads();
+        // ---- P3 (serial): second running sum ----
+        if (warp == 0 && my_slot >= 0 && s_valid[lane]) sum2 = running_sum_serial(sum2, tDm, tM, tY, h, D, P, lane);
+        __syncthreads();
+        // ---- P4 (parallel): DC output y = x[delayed] - ma2 (src/utils.h:145-149), running |y| maximum,
+        //      window peak, desired gain (audioprocessing.cpp:48-52) ----
+        for (int ci = warp; ci < cpb; ci += kTailWarps) {
+            if (s_slot[ci] < 0 || !s_valid[ci]) continue;
+            float carry = 0.f;
+            for (int base = 0; base < h; base += 32) {
+                const int j = base + lane;
+                float y = 0.f, m = 0.f;
+                if (j < h) {
+                    const float ma2 = __fdiv_rn(tY[j * P + ci], Df);
+                    const float xd = (j + 1 < D) ? tDx[(j + 1) * P + ci] : tA[(j + 1 - D) * P + ci];
+                    y = __fsub_rn(xd, ma2);
+                    m = fabsf(y);
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {  // inclusive prefix max
+                    const float other = __shfl_up_sync(0xffffffffu, m, o);
+                    if (lane >= o) m = fmaxf(m, other);
+                }
+                m = fmaxf(m, carry);
+                if (j < h) {
+                    tY[j * P + ci] = y;
+                    const float peak = fmaxf(tP[j * P + ci], m);
+                    tP[j * P + ci] = __fdiv_rn(ca.desired, __fadd_rn(peak, 1e-10f));
+                }
+                carry = __shfl_sync(0xffffffffu, m, 31);
+            }
+            if (lane == 0) s_pmax[ci] = carry;
+        }
+        __syncthreads();
+        // ---- P5 (serial): attack/release recurrence on the gain, audioprocessing.cpp:54-63 ----
         if (warp == 0 && my_slot >= 0 && s_valid[lane]) {
             const int ci = lane;
-            const float Df = (float)D;
-            // DC blocker: src/utils.h:80-85,145-149.  xe = [dc_x | audio], me = [dc_m | ma1]
-            for (int j = 0; j < h; j++) {
-                const float xin = tA[j * kPitch + ci];
-                const float old1 = (j < D) ? tDx[j * kPitch + ci] : tA[(j - D) * kPitch + ci];
-                sum1 = __fadd_rn(__fadd_rn(sum1, -old1), xin);
-                const float ma1 = __fdiv_rn(sum1, Df);
-                tM[j * kPitch + ci] = ma1;
-                const float old2 = (j < D) ? tDm[j * kPitch + ci] : tM[(j - D) * kPitch + ci];
-                sum2 = __fadd_rn(__fadd_rn(sum2, -old2), ma1);
-                const float ma2 = __fdiv_rn(sum2, Df);
-                const float xd = (j + 1 < D) ? tDx[(j + 1) * kPitch + ci] : tA[(j + 1 - D) * kPitch + ci];
-                tY[j * kPitch + ci] = __fsub_rn(xd, ma2);
-            }
-            // AGC: audioprocessing.cpp:40-68 with the sliding |x| maximum taken from chunk maxima
-            const int c0 = s_ca[ci];
-            const int F = (int)(t0 / h);
-            const float *cmax = ca.agc_cmax + (size_t)my_slot * NC;
-            float mfull[2];
-            for (int rr = 0; rr < 2; rr++) {
-                float m = 0.f;
-                for (int c = c0 + rr + 1; c <= F - 1; c++) m = fmaxf(m, cmax[((c % NC) + NC) % NC]);
-                mfull[rr] = m;
-            }
-            float pmax = 0.f;
-            for (int j = 0; j < h; j++) {
-                const float yv = tY[j * kPitch + ci];
-                pmax = fmaxf(pmax, fabsf(yv));
-                const long long lo = t0 + j - L + 1;  // oldest sample in the window
-                float outv = 0.f;
-                if (t0 + j + 1 >= L) {
-                    const int c = floordiv(lo, h);
-                    const int col = (int)(lo - (long long)c * h);
-                    const int rr = c - c0;  // 0 or 1
-                    const float cur = tO[(rr * h + col) * kPitch + ci];
-                    const float peak = fmaxf(fmaxf(tS[(rr * h + col) * kPitch + ci], mfull[rr]), pmax);
-                    const float desired = __fdiv_rn(ca.desired, __fadd_rn(peak, 1e-10f));
-                    if (desired < gain) gain = __fsub_rn(gain, __fmul_rn(ca.attack, __fsub_rn(gain, desired)));
-                    else gain = __fadd_rn(gain, __fmul_rn(ca.release, __fsub_rn(desired, gain)));
-                    outv = __fmul_rn(cur, gain);
+            const float att = ca.attack, rel = ca.release;
+            // outputs stay 0 until the look-ahead buffer is full (audioprocessing.cpp:45,64-66)
+            long long first = (long long)L - 1 - t0;
+            if (first < 0) first = 0;
+            if (first > h) first = h;
+            int j = 0;
+            for (; j < (int)first; j++) tC[j * P + ci] = 0.f;
+            for (; j + 4 <= h; j += 4) {
+                float d[4], c[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    d[u] = tP[(j + u) * P + ci];
+                    c[u] = tC[(j + u) * P + ci];
                 }
-                tA[j * kPitch + ci] = outv;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float ga = __fsub_rn(gain, __fmul_rn(att, __fsub_rn(gain, d[u])));
+                    const float gr = __fadd_rn(gain, __fmul_rn(rel, __fsub_rn(d[u], gain)));
+                    gain = (d[u] < gain) ? ga : gr;
+                    c[u] = __fmul_rn(c[u], gain);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) tC[(j + u) * P + ci] = c[u];
             }
-            ca.agc_cmax[(size_t)my_slot * NC + (F % NC)] = pmax;
+            for (; j < h; j++) {
+                const float desired = tP[j * P + ci];
+                if (desired < gain) gain = __fsub_rn(gain, __fmul_rn(att, __fsub_rn(gain, desired)));
+                else gain = __fadd_rn(gain, __fmul_rn(rel, __fsub_rn(desired, gain)));
+                tC[j * P + ci] = __fmul_rn(tC[j * P + ci], gain);
+            }
             t0 += h;
         }
         __syncthreads();
-        // ---- write back (lanes along j) ----
-        for (int ci = warp; ci < cpb; ci += kTailThreads / 32) {
+        // ---- P6 (parallel): write back ----
+        for (int ci = warp; ci < cpb; ci += kTailWarps) {
             const int slot = s_slot[ci];
             if (slot < 0) continue;
             int *pcm = ca.pcm + ((size_t)f * ca.max_clients + slot) * h;
@@ -467,41 +611,33 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
                 continue;
             }
             if (lane == 0) ca.valid[(size_t)f * ca.max_clients + slot] = 1;
+            const long long Fc = s_t0[ci] / h;
+            const int row = (int)(Fc % NC);
+            float *dst = ca.agc_ring + ((size_t)slot * NC + row) * h;
             for (int j = lane; j < h; j += 32) {
                 // dsp.cpp:152-165 with mult = 65536/4
-                const float x = tA[j * kPitch + ci];
+                const float x = tC[j * P + ci];
                 const float t = __fadd_rn(__fmul_rn(x, 16384.f), 32768.5f);
                 int v = __float2int_rz(t) - 32768;
                 v = max(min(v, 32767), -32768);
                 pcm[j] = v;
+                dst[j] = tY[j * P + ci];
             }
-            // DC state: last D of [dc_x | audio_in] and [dc_m | ma1]; audio_in was overwritten in tA by
-            // the AGC output, so re-read it from audio_pre (L2-resident)
-            const float *a = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
+            if (lane == 0) ca.agc_cmax[(size_t)slot * NC + row] = s_pmax[ci];
+            // DC state: last D of [dc_x | audio_in] and [dc_m | ma1]
             for (int j = lane; j < D; j += 32) {
-                const int src = h + j;  // index into the (D + h)-long concatenation, minus D offset below
+                const int src = h + j;  // index into the (D + h)-long concatenation
                 float nx, nm;
                 if (src >= D) {
-                    nx = a[src - D];
-                    nm = tM[(src - D) * kPitch + ci];
+                    nx = tA[(src - D) * P + ci];
+                    nm = tM[(src - D) * P + ci];
                 } else {
-                    nx = tDx[src * kPitch + ci];
-                    nm = tDm[src * kPitch + ci];
+                    nx = tDx[src * P + ci];
+                    nm = tDm[src * P + ci];
                 }
                 ca.dc_x[(size_t)slot * D + j] = nx;
                 ca.dc_m[(size_t)slot * D + j] = nm;
             }
-        }
-        // AGC ring row of this frame: needs each client's chunk index -> done by a second sweep
-        __syncthreads();
-        if (warp == 0) s_ca[lane] = (my_slot >= 0 && s_valid[lane]) ? (int)(((t0 / h) - 1) % NC) : -1;
-        __syncthreads();
-        for (int ci = warp; ci < cpb; ci += kTailThreads / 32) {
-            const int slot = s_slot[ci];
-            const int row = s_ca[ci];
-            if (slot < 0 || row < 0) continue;
-            float *dst = ca.agc_ring + ((size_t)slot * NC + row) * h;
-            for (int j = lane; j < h; j += 32) dst[j] = tY[j * kPitch + ci];
         }
         __syncthreads();
     }

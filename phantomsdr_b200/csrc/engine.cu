@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,11 +43,15 @@ struct SubPlan {  // S = RA * RB points per sub-transform, T columns per CTA
     int S, RA, RB, T;
 };
 
-SubPlan sub_plan(int S) {
+SubPlan sub_plan(int S, const char *tile_env) {
+    int t1024 = 16;
+    if (const char *v = getenv(tile_env)) {  // tuning aid: B200_TILE1 / B200_TILE2 = 8 | 16 for the 1024-point passes
+        if (atoi(v) == 8) t1024 = 8;
+    }
     switch (S) {
     case 256: return {256, 16, 16, 32};
     case 512: return {512, 16, 32, 16};
-    case 1024: return {1024, 32, 32, 16};
+    case 1024: return {1024, 32, 32, t1024};
     }
     return {0, 0, 0, 0};
 }
@@ -99,6 +104,7 @@ struct b200_engine {
     float2 *d_Y = nullptr, *d_Z = nullptr, *d_spec = nullptr, *spec_bound = nullptr;
     int8_t *d_quant = nullptr;
     float *d_ptop = nullptr;
+    float *d_pscratch = nullptr;
     float2 *d_twA1 = nullptr, *d_twA2 = nullptr, *d_TL = nullptr, *d_TH = nullptr, *d_TLr = nullptr, *d_THr = nullptr;
     size_t spec_stride = 0, pyr_stride = 0, pyr_bytes = 0;
     int batch = 1;
@@ -118,6 +124,7 @@ struct b200_engine {
     int opt_reload_both = 0;
     int opt_mirror = 3;
     int opt_stage_mask = 7;
+    int opt_fused_pyramid = 1;
 
     int npeers = 0;
     float2 *peers[kMaxPeers] = {};
@@ -132,7 +139,6 @@ struct b200_engine {
     int *d_order = nullptr;
     int tail_cpb = 32;
     size_t tail_smem = 0;
-    int demod_wpb = 8;
     int last_client_frames = 0;
 
     uint64_t launches = 0;
@@ -152,50 +158,65 @@ struct b200_engine {
 
 namespace {
 
-template <int RA, int RB, int T> int launch_pass1(b200_engine *e, const FwdParams &p, int frames) {
+template <int RA, int RB, int T, bool RAW> int launch_pass1(b200_engine *e, const FwdParams &p, int frames) {
     constexpr int threads = T * CMax<RA, RB>::v;
     constexpr int PAD = (T < 16) ? (16 - T) : 0;
     constexpr size_t smem = sizeof(float2) * RB * (RA * T + PAD);
     if (frames == 0) {  // preparation call from plan time
-        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
     dim3 grid(p.N2 / T, frames);
-    fft_pass1_kernel<RA, RB, T><<<grid, threads, smem, e->stream>>>(p);
+    fft_pass1_kernel<RA, RB, T, RAW><<<grid, threads, smem, e->stream>>>(p);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-template <int RA, int RB, int T> int launch_pass2(b200_engine *e, const FwdParams &p, int frames) {
+template <int RA, int RB, int T, bool FUSE> int launch_pass2(b200_engine *e, const FwdParams &p, int frames) {
     constexpr int threads = T * CMax<RA, RB>::v;
     constexpr size_t smem = sizeof(float2) * RB * (RA * T + 1);
+    static_assert(!FUSE || sizeof(float) * RA * RB * (T + 4) <= smem, "power tile must fit in the exchange buffer");
     if (frames == 0) {  // preparation call from plan time
-        CU(cudaFuncSetAttribute(fft_pass2_kernel<RA, RB, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fft_pass2_kernel<RA, RB, T, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
     dim3 grid(p.N1 / T, frames);
-    fft_pass2_kernel<RA, RB, T><<<grid, threads, smem, e->stream>>>(p);
+    fft_pass2_kernel<RA, RB, T, FUSE><<<grid, threads, smem, e->stream>>>(p);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-int dispatch_pass1(b200_engine *e, const FwdParams &p, int frames) {
-    switch (e->sp1.S) {
-    case 256: return launch_pass1<16, 16, 32>(e, p, frames);
-    case 512: return launch_pass1<16, 32, 16>(e, p, frames);
-    case 1024: return launch_pass1<32, 32, 16>(e, p, frames);
-    }
-    return fail(B200_ENOTSUP, "no pass-1 kernel for sub-transform %d", e->sp1.S);
+template <bool RAW> int dispatch_pass1_fmt(b200_engine *e, const FwdParams &p, int frames) {
+    const SubPlan &sp = e->sp1;
+    if (sp.S == 256) return launch_pass1<16, 16, 32, RAW>(e, p, frames);
+    if (sp.S == 512) return launch_pass1<16, 32, 16, RAW>(e, p, frames);
+    if (sp.S == 1024 && sp.T == 16) return launch_pass1<32, 32, 16, RAW>(e, p, frames);
+    if (sp.S == 1024 && sp.T == 8) return launch_pass1<32, 32, 8, RAW>(e, p, frames);
+    return fail(B200_ENOTSUP, "no pass-1 kernel for sub-transform %d", sp.S);
 }
-int dispatch_pass2(b200_engine *e, const FwdParams &p, int frames) {
-    switch (e->sp2.S) {
-    case 256: return launch_pass2<16, 16, 32>(e, p, frames);
-    case 512: return launch_pass2<16, 32, 16>(e, p, frames);
-    case 1024: return launch_pass2<32, 32, 16>(e, p, frames);
+int dispatch_pass1(b200_engine *e, const FwdParams &p, int frames) {
+    if (frames == 0) {
+        int rc = dispatch_pass1_fmt<false>(e, p, 0);
+        return rc ? rc : dispatch_pass1_fmt<true>(e, p, 0);
     }
-    return fail(B200_ENOTSUP, "no pass-2 kernel for sub-transform %d", e->sp2.S);
+    return p.in_format == FMT_F32 ? dispatch_pass1_fmt<false>(e, p, frames) : dispatch_pass1_fmt<true>(e, p, frames);
+}
+template <bool FUSE> int dispatch_pass2_f(b200_engine *e, const FwdParams &p, int frames) {
+    const SubPlan &sp = e->sp2;
+    if (sp.S == 256) return launch_pass2<16, 16, 32, FUSE>(e, p, frames);
+    if (sp.S == 512) return launch_pass2<16, 32, 16, FUSE>(e, p, frames);
+    if (sp.S == 1024 && sp.T == 16) return launch_pass2<32, 32, 16, FUSE>(e, p, frames);
+    if (sp.S == 1024 && sp.T == 8) return launch_pass2<32, 32, 8, FUSE>(e, p, frames);
+    return fail(B200_ENOTSUP, "no pass-2 kernel for sub-transform %d", sp.S);
+}
+int dispatch_pass2(b200_engine *e, const FwdParams &p, int frames, bool fuse) {
+    if (frames == 0) {
+        int rc = dispatch_pass2_f<false>(e, p, 0);
+        return rc ? rc : dispatch_pass2_f<true>(e, p, 0);
+    }
+    return fuse ? dispatch_pass2_f<true>(e, p, frames) : dispatch_pass2_f<false>(e, p, frames);
 }
 
 // forward FFT + pyramid for `frames` consecutive frames starting at ring hop `hop0`
@@ -233,10 +254,18 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         p.additional = 0;
         p.npeers = 0;
     }
+    const bool fuse = !e->is_real && e->opt_fused_pyramid;
+    int base_level = 0;
+    while ((1 << base_level) < e->sp2.T) base_level++;
+    p.quant = e->d_quant;
+    p.pyr_stride = e->pyr_stride;
+    p.pscratch = e->d_pscratch;
+    p.levels = e->levels;
+    p.size_log2 = e->size_log2;
     int rc = 0;
     if (e->opt_stage_mask & 1) rc = dispatch_pass1(e, p, frames);
     if (rc) return rc;
-    if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames);
+    if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames, fuse);
     if (rc) return rc;
     if (!(e->opt_stage_mask & 4)) return 0;
 
@@ -252,20 +281,27 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     q.log2R = log2R;
     q.levels = e->levels;
     q.size_log2 = e->size_log2;
-    q.is_real = e->is_real ? 1 : 0;
     q.scale = 1.0f / (float)e->size;
     q.TLr = e->d_TLr;
     q.THr = e->d_THr;
+    q.pscratch = e->d_pscratch;
+    q.base_level = fuse ? base_level : 0;
+    q.ntiles = e->sp1.S / e->sp2.T;
+    q.N2 = e->sp2.S;
     q.npeers = e->is_real ? e->npeers : 0;
     for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i];
-    dim3 grid((unsigned)(e->R / 1024), frames);
-    pyramid_kernel<<<grid, 256, 0, e->stream>>>(q);
-    e->launches++;
-    CU(cudaGetLastError());
-    if (e->levels > 11) {
-        pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q);
+    if (e->levels > q.base_level) {
+        dim3 grid((unsigned)((e->R >> q.base_level) / 1024), frames);
+        if (e->is_real) pyramid_kernel<PYR_R2C><<<grid, 256, 0, e->stream>>>(q);
+        else if (fuse) pyramid_kernel<PYR_SCRATCH><<<grid, 256, 0, e->stream>>>(q);
+        else pyramid_kernel<PYR_SPEC><<<grid, 256, 0, e->stream>>>(q);
         e->launches++;
         CU(cudaGetLastError());
+        if (e->levels - q.base_level > 11) {
+            pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q, q.base_level);
+            e->launches++;
+            CU(cudaGetLastError());
+        }
     }
     return 0;
 }
@@ -289,8 +325,8 @@ int plan_common(b200_engine *e, bool is_real) {
         return fail(B200_ENOTSUP, "fft size %zu (%s) not supported: complex transform length must be 2^16..2^20", e->size,
                     is_real ? "r2c" : "c2c");
     }
-    e->sp1 = sub_plan(s1);
-    e->sp2 = sub_plan(s2);
+    e->sp1 = sub_plan(s1, "B200_TILE1");
+    e->sp2 = sub_plan(s2, "B200_TILE2");
     if (e->levels < 1) return fail(B200_EINVAL, "downsample_levels must be >= 1");
     if ((e->R >> (e->levels - 1)) < 1) return fail(B200_EINVAL, "too many downsample levels for %zu bins", e->R);
     e->hop_samples = is_real ? e->size / 2 : e->size;  // scalar samples per hop
@@ -320,7 +356,7 @@ int plan_common(b200_engine *e, bool is_real) {
         FwdParams none{};
         int rc = dispatch_pass1(e, none, 0);
         if (rc) return rc;
-        rc = dispatch_pass2(e, none, 0);
+        rc = dispatch_pass2(e, none, 0, false);
         if (rc) return rc;
     }
     e->planned = true;
@@ -333,6 +369,8 @@ int alloc_batch(b200_engine *e, int frames) {
     if (e->d_spec) cudaFree(e->d_spec);
     if (e->d_quant) cudaFree(e->d_quant);
     if (e->d_ptop) cudaFree(e->d_ptop);
+    if (e->d_pscratch) cudaFree(e->d_pscratch);
+    e->d_pscratch = nullptr;
     e->d_Y = e->d_Z = e->d_spec = nullptr;
     e->d_quant = nullptr;
     e->d_ptop = nullptr;
@@ -343,6 +381,7 @@ int alloc_batch(b200_engine *e, int frames) {
     CU(cudaMalloc(&e->d_quant, e->pyr_stride * frames));
     CU(cudaMemset(e->d_quant, 0, e->pyr_stride * frames));
     CU(cudaMalloc(&e->d_ptop, sizeof(float) * std::max<size_t>(1, e->R / 1024) * frames));
+    CU(cudaMalloc(&e->d_pscratch, sizeof(float) * (size_t)(e->sp1.S / e->sp2.T) * e->sp2.S * frames));
     e->batch = frames;
     return 0;
 }
@@ -390,17 +429,39 @@ std::vector<int> factorize(int n) {
     return r;
 }
 
-template <int WPB> int launch_demod(b200_engine *e, const ClientLaunch &cl) {
-    const size_t smem = sizeof(float2) * 2 * e->ca.n * WPB;
+constexpr int kDemodThreads = 128;
+
+int launch_demod(b200_engine *e, const ClientLaunch &cl) {
+    const size_t smem = sizeof(float2) * 2 * e->ca.n;
     if (cl.nactive == 0) {  // preparation call from clients_create
-        CU(cudaFuncSetAttribute(client_demod_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(client_demod_kernel<kDemodThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
-    const int blocks = (cl.nactive + WPB - 1) / WPB;
-    client_demod_kernel<WPB><<<blocks, WPB * 32, smem, e->stream>>>(e->ca, cl);
+    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, e->stream>>>(e->ca, cl);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
+}
+
+template <int KB> int launch_tail_kb(b200_engine *e, const ClientLaunch &cl) {
+    if (cl.nactive == 0) {  // preparation call from clients_create
+        CU(cudaFuncSetAttribute(client_tail_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tail_smem));
+        return 0;
+    }
+    const int blocks = (cl.nactive + cl.cpb - 1) / cl.cpb;
+    client_tail_kernel<KB><<<blocks, kTailThreads, e->tail_smem, e->stream>>>(e->ca, cl);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int launch_tail(b200_engine *e, const ClientLaunch &cl) {
+    const int kb = (e->ca.h + 31) / 32;
+    if (kb <= 2) return launch_tail_kb<2>(e, cl);
+    if (kb <= 4) return launch_tail_kb<4>(e, cl);
+    if (kb <= 6) return launch_tail_kb<6>(e, cl);
+    if (kb <= 9) return launch_tail_kb<9>(e, cl);
+    if (kb <= 12) return launch_tail_kb<12>(e, cl);
+    return launch_tail_kb<0>(e, cl);
 }
 
 int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
@@ -439,18 +500,10 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     cl.order = e->d_order;
     cl.nactive = (int)e->order.size();
     cl.cpb = e->tail_cpb;
-    int rc;
-    switch (e->demod_wpb) {
-    case 8: rc = launch_demod<8>(e, cl); break;
-    case 4: rc = launch_demod<4>(e, cl); break;
-    case 2: rc = launch_demod<2>(e, cl); break;
-    default: rc = launch_demod<1>(e, cl); break;
-    }
+    int rc = launch_demod(e, cl);
     if (rc) return rc;
-    const int blocks = (cl.nactive + cl.cpb - 1) / cl.cpb;
-    client_tail_kernel<<<blocks, kTailThreads, e->tail_smem, e->stream>>>(e->ca, cl);
-    e->launches++;
-    CU(cudaGetLastError());
+    rc = launch_tail(e, cl);
+    if (rc) return rc;
     // one-shot reset flags have been consumed by this launch
     bool any = false;
     for (auto &s : e->slots)
@@ -530,7 +583,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec, e->d_quant, e->d_ptop, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
+    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec, e->d_quant, e->d_ptop, e->d_pscratch, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
@@ -620,6 +673,7 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_RELOAD_BOTH: e->opt_reload_both = value ? 1 : 0; return 0;
     case B200_OPT_HOST_MIRROR: e->opt_mirror = value & 3; return 0;
     case B200_OPT_STAGE_MASK: e->opt_stage_mask = value & 7; return 0;
+    case B200_OPT_FUSED_PYRAMID: e->opt_fused_pyramid = value ? 1 : 0; return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
         if (value != e->in_format) {
@@ -809,24 +863,17 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     e->slots.assign(mc, ClientSlot{});
     e->mids.assign(mc, 0.0);
     // launch geometry
-    e->demod_wpb = 8;
-    while (e->demod_wpb > 1 && sizeof(float2) * 2 * ca.n * e->demod_wpb > 160 * 1024) e->demod_wpb /= 2;
     if (sizeof(float2) * 2 * ca.n > 200 * 1024) return fail(B200_ENOTSUP, "audio_fft_size %d too large", ca.n);
-    e->tail_cpb = 32;
-    auto tail_bytes = [&](int cpb) { return sizeof(float) * (size_t)(7 * ca.h + 2 * ca.D) * (cpb + 1); };
+    e->tail_cpb = kTailMaxCpb;
+    auto tail_bytes = [&](int cpb) { return sizeof(float) * (size_t)(5 * ca.h + 2 * ca.D) * (cpb + 1); };
     while (e->tail_cpb > 1 && tail_bytes(e->tail_cpb) > 200 * 1024) e->tail_cpb /= 2;
     if (tail_bytes(e->tail_cpb) > 200 * 1024) return fail(B200_ENOTSUP, "audio_fft_size %d too large for the tail kernel", ca.n);
     e->tail_smem = tail_bytes(e->tail_cpb);
-    CU(cudaFuncSetAttribute(client_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tail_smem));
     {
         ClientLaunch none{};
-        int rc;
-        switch (e->demod_wpb) {
-        case 8: rc = launch_demod<8>(e, none); break;
-        case 4: rc = launch_demod<4>(e, none); break;
-        case 2: rc = launch_demod<2>(e, none); break;
-        default: rc = launch_demod<1>(e, none); break;
-        }
+        int rc = launch_demod(e, none);
+        if (rc) return rc;
+        rc = launch_tail(e, none);
         if (rc) return rc;
     }
     e->have_clients = true;

@@ -47,6 +47,12 @@ struct FwdParams {
     const float2 *TH;        // W_M^(1024 j)
     int npeers;
     float2 *peers[kMaxPeers];  // extra spectrum destinations (NVLink peer memory)
+    // fused waterfall epilogue of pass 2 (c2c): levels 0..log2(T)-1 straight from the FFT registers
+    int8_t *quant;           // pyramid [frames][pyr_stride]
+    size_t pyr_stride;
+    float *pscratch;         // [frames][N1/T][N2] power sums of level log2(T)
+    int levels;
+    int size_log2;
 };
 
 template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
@@ -73,9 +79,8 @@ __device__ __forceinline__ float2 load_sample(const void *hop, int fmt, size_t e
 // ------------------------------------------------------------------------------------------------
 // pass 1: grid (N2/T, frames), block T*max(RA,RB)
 // ------------------------------------------------------------------------------------------------
-template <int RA, int RB, int T>
+template <int RA, int RB, int T, bool RAW>
 __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const FwdParams p) {
-    constexpr int TPC = CMax<RA, RB>::v;
     constexpr int PAD = (T < 16) ? (16 - T) : 0;   // keep the two r-rows of a half-warp on disjoint banks
     constexpr int ROW = RA * T + PAD;
     extern __shared__ float2 sm[];
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
 
     if (r < RB) {
         float2 v[RA];
-        const int fmt = p.in_format;
+        const int fmt = RAW ? p.in_format : FMT_F32;  // float32 input: a compile-time constant, loads batch freely
 #pragma unroll
         for (int j = 0; j < RA; j++) {
             const size_t idx = (size_t)(r + RB * j) * N2 + n2;  // complex element within the frame
@@ -142,12 +147,53 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
 }
 
 // ------------------------------------------------------------------------------------------------
+// waterfall quantiser - bit-exact restatement of vec_log2 / power_and_quantize (src/fft_impl.cpp:14-44).
+// Every float op is an explicit round-to-nearest intrinsic (no FMA contraction) in source order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vec_log2_dev(float val, int power_offset) {
+    unsigned bits = __float_as_uint(val);
+    float log_val = __fadd_rn((float)((int)((bits >> 23) & 0xFF) - 128), (float)power_offset);
+    bits &= ~(255u << 23);
+    bits += 127u << 23;
+    val = __uint_as_float(bits);
+    float poly = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(-0.34484843f, val), 2.02466578f), val), 0.67487759f);
+    return __fadd_rn(log_val, poly);
+}
+__device__ __forceinline__ int quantize_dev(float power, int power_offset) {
+    float v = __fadd_rn(__fmul_rn(__fmul_rn(vec_log2_dev(power, power_offset), 0.3010299956639812f), 20.f), 127.f);
+    v = (v > -128.f) ? v : -128.f;        // std::max(-128.f, v); NaN -> -128
+    int t = __float2int_rz(v);            // C truncation
+    return t & 0xFF;                      // int8 store keeps the low byte (wraps above 127 like x86)
+}
+
+// ------------------------------------------------------------------------------------------------
 // pass 2: grid (N1/T, frames), block T*max(RA,RB)
 // ------------------------------------------------------------------------------------------------
-template <int RA, int RB, int T>
+template <int NB> __device__ __forceinline__ void store_packed(int8_t *dst, const unsigned *w) {
+    // NB quantised bytes packed little-endian in w[]; dst is NB-aligned
+    if constexpr (NB >= 16) {
+#pragma unroll
+        for (int i = 0; i < NB / 16; i++)
+            reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    } else if constexpr (NB == 8) {
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    } else if constexpr (NB == 4) {
+        *reinterpret_cast<unsigned *>(dst) = w[0];
+    } else if constexpr (NB == 2) {
+        *reinterpret_cast<unsigned short *>(dst) = (unsigned short)w[0];
+    } else {
+        *dst = (int8_t)w[0];
+    }
+}
+
+template <int T> struct Log2 { static constexpr int v = 1 + Log2<T / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+template <int RA, int RB, int T, bool FUSE>
 __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const FwdParams p) {
     constexpr int TPC = CMax<RA, RB>::v;
     constexpr int ROW = RA * T + 1;  // odd stride: lanes along r hit distinct banks
+    constexpr int PP = T + 4;        // pitch of the power tile (floats): float4 reads stay conflict-free
     extern __shared__ float2 sm[];
 
     const int tid = threadIdx.x;
@@ -173,6 +219,7 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
         }
     }
     __syncthreads();
+    float pw[RB];
     {   // stage B: lanes along u1 (contiguous in the spectrum)
         const int c = tid % T;
         const int q = tid / T;
@@ -196,70 +243,112 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
                     po[k] = val;
                     if (k < (size_t)p.additional) po[M + k] = val;
                 }
+                if constexpr (FUSE) pw[s] = __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
             }
+        }
+    }
+    if constexpr (FUSE) {
+        // Waterfall epilogue (src/fft_impl.cpp:24-61,146-173): |X|^2 of this CTA's T x N2 bins goes through
+        // shared memory so that one thread owns one display run of T bins and writes whole words.
+        float *pt = reinterpret_cast<float *>(sm);
+        __syncthreads();  // everyone is done reading the exchange buffer
+        {
+            const int c = tid % T;
+            const int q = tid / T;
+            if (q < RA) {
+#pragma unroll
+                for (int s = 0; s < RB; s++) pt[(q + RA * s) * PP + c] = pw[s];
+            }
+        }
+        __syncthreads();
+        constexpr int LT = Log2<T>::v;
+        const int L = p.levels;
+        int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
+        float *scr = p.pscratch + ((size_t)frame * (N1 / T) + blockIdx.x) * N2;
+        for (int u2 = tid; u2 < N2; u2 += T * TPC) {
+            // display bin d = u1 + N1 * ((u2 + N2/2) mod N2): the base_idx = N/2+1 shift of fft_impl.cpp:148-160
+            const unsigned d2 = (u2 + (N2 >> 1)) & (N2 - 1);
+            const size_t dbase = (size_t)blockIdx.x * T + (size_t)N1 * d2;
+            float v[T];
+#pragma unroll
+            for (int i = 0; i < T / 4; i++) {
+                const float4 f = *reinterpret_cast<const float4 *>(pt + u2 * PP + 4 * i);
+                v[4 * i] = f.x;
+                v[4 * i + 1] = f.y;
+                v[4 * i + 2] = f.z;
+                v[4 * i + 3] = f.w;
+            }
+            size_t lvl_off = 0;
+            const size_t R = M;
+            static_for<LT>([&](auto lvc) {
+                constexpr int lv = decltype(lvc)::value;
+                constexpr int CNT = T >> lv;
+                if (lv < L) {
+                    unsigned w[(CNT + 3) / 4];
+#pragma unroll
+                    for (int i = 0; i < (CNT + 3) / 4; i++) w[i] = 0;
+#pragma unroll
+                    for (int i = 0; i < CNT; i++)
+                        w[i / 4] |= (unsigned)quantize_dev(v[i], p.size_log2 - lv) << (8 * (i % 4));
+                    store_packed<CNT>(quant + lvl_off + (dbase >> lv), w);
+                }
+                lvl_off += R >> lv;
+#pragma unroll
+                for (int i = 0; i < CNT / 2; i++) v[i] = __fadd_rn(v[2 * i], v[2 * i + 1]);
+            });
+            scr[d2] = v[0];  // level LT power, consumed by pyramid_kernel<PYR_SCRATCH>
         }
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// waterfall quantiser - bit-exact restatement of vec_log2 / power_and_quantize (src/fft_impl.cpp:14-44).
-// Every float op is an explicit round-to-nearest intrinsic (no FMA contraction) in source order.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float vec_log2_dev(float val, int power_offset) {
-    unsigned bits = __float_as_uint(val);
-    float log_val = __fadd_rn((float)((int)((bits >> 23) & 0xFF) - 128), (float)power_offset);
-    bits &= ~(255u << 23);
-    bits += 127u << 23;
-    val = __uint_as_float(bits);
-    float poly = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(-0.34484843f, val), 2.02466578f), val), 0.67487759f);
-    return __fadd_rn(log_val, poly);
-}
-__device__ __forceinline__ int quantize_dev(float power, int power_offset) {
-    float v = __fadd_rn(__fmul_rn(__fmul_rn(vec_log2_dev(power, power_offset), 0.3010299956639812f), 20.f), 127.f);
-    v = (v > -128.f) ? v : -128.f;        // std::max(-128.f, v); NaN -> -128
-    int t = __float2int_rz(v);            // C truncation
-    return t & 0xFF;                      // int8 store keeps the low byte (wraps above 127 like x86)
-}
+enum { PYR_SPEC = 0, PYR_R2C = 1, PYR_SCRATCH = 2 };
 
 struct PyrParams {
-    float2 *spec;            // spectrum (c2c: input, already normalised; r2c: OUTPUT written here)
+    float2 *spec;            // spectrum (PYR_SPEC: input, already normalised; PYR_R2C: OUTPUT written here)
     size_t spec_stride;
-    const float2 *Z;         // r2c: packed half-size transform (unnormalised), [frames][M]
+    const float2 *Z;         // PYR_R2C: packed half-size transform (unnormalised), [frames][M]
     int8_t *quant;           // pyramid output [frames][pyr_stride]
     size_t pyr_stride;
-    float *ptop;             // [frames][R/1024] level-10 power sums (only when levels > 11)
+    float *ptop;             // [frames][(R >> base_level) / 1024] sums ten levels above the base (deep pyramids only)
     int log2R;               // display bins R = 1 << log2R
     int levels;
     int size_log2;           // round(log2(size)) + brightness_offset
-    int is_real;
-    float scale;             // r2c: 1/size
-    const float2 *TLr;       // r2c: W_size^j, j < 1024
-    const float2 *THr;       // r2c: W_size^(1024 j)
+    float scale;             // PYR_R2C: 1/size
+    const float2 *TLr;       // PYR_R2C: W_size^j, j < 1024
+    const float2 *THr;       // PYR_R2C: W_size^(1024 j)
+    // PYR_SCRATCH: level `base_level` power sums left by the fused pass-2 epilogue, [frames][ntiles][N2],
+    // logical index i = tile + ntiles * d2
+    const float *pscratch;
+    int base_level;
+    int ntiles, N2;
     int npeers;
     float2 *peers[kMaxPeers];
 };
 
-// grid (R/1024, frames), block 256: each thread owns 4 consecutive display bins.
-__global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
-    __shared__ float warp_sum[8];
+// grid ((R >> base_level)/1024, frames), block 256: each thread owns 4 consecutive entries of the base level
+// and the block reduces up to ten more levels (pairwise sums, src/fft_impl.cpp:45-61,162-172).
+template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+    __shared__ float warp_sum_s[8];
     const int tid = threadIdx.x;
     const int frame = blockIdx.y;
     const size_t R = (size_t)1 << p.log2R;
-    const size_t d0 = (size_t)blockIdx.x * 1024 + 4 * tid;
-    float2 *spec = p.spec + (size_t)frame * p.spec_stride;
+    const int B = (MODE == PYR_SCRATCH) ? p.base_level : 0;
+    const size_t d0 = (size_t)blockIdx.x * 1024 + 4 * tid;  // index at level B
     int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
 
     float pw[4];
-    if (!p.is_real) {
+    if constexpr (MODE == PYR_SPEC) {
         // display bin d <-> FFT bin (d + R/2 + 1) mod R   (src/fft_impl.cpp:148-160)
+        const float2 *spec = p.spec + (size_t)frame * p.spec_stride;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const size_t k = (d0 + i + (R >> 1) + 1) & (R - 1);
             const float2 x = spec[k];
             pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
         }
-    } else {
+    } else if constexpr (MODE == PYR_R2C) {
         // r2c split: X[k] = (Z[k] + conj(Z[M-k]))/2 - (i/2) W_size^k (Z[k] - conj(Z[M-k])), M = R
+        float2 *spec = p.spec + (size_t)frame * p.spec_stride;
         const float2 *Z = p.Z + (size_t)frame * R;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -284,27 +373,38 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
             for (int pe = 0; pe < p.npeers; pe++) (p.peers[pe] + (size_t)frame * p.spec_stride)[k] = x;
             pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
         }
+    } else {
+        const float *scr = p.pscratch + (size_t)frame * p.ntiles * p.N2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const size_t idx = d0 + i;
+            const size_t tile = idx % p.ntiles, d2 = idx / p.ntiles;
+            pw[i] = scr[tile * p.N2 + d2];
+        }
     }
-    const int L = p.levels;
-    const int off = p.size_log2;
-    // level 0
+    const int L = p.levels - B;  // levels still to produce, counted from the base
+    const int off = p.size_log2 - B;
+    size_t lvl_off = 0;          // byte offset of level B
+    for (int i = 0; i < B; i++) lvl_off += R >> i;
+    const size_t RB_ = R >> B;   // entries at the base level
+    if (L <= 0) return;
     {
         unsigned packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) packed |= (unsigned)quantize_dev(pw[i], off) << (8 * i);
-        *reinterpret_cast<unsigned *>(quant + d0) = packed;
+        *reinterpret_cast<unsigned *>(quant + lvl_off + d0) = packed;
     }
-    size_t lvl_off = R;  // byte offset of level 1
+    lvl_off += RB_;
     if (L > 1) {
         const float s0 = __fadd_rn(pw[0], pw[1]), s1 = __fadd_rn(pw[2], pw[3]);
         const unsigned short pk = (unsigned short)(quantize_dev(s0, off - 1) | (quantize_dev(s1, off - 1) << 8));
         *reinterpret_cast<unsigned short *>(quant + lvl_off + (d0 >> 1)) = pk;
-        lvl_off += R >> 1;
+        lvl_off += RB_ >> 1;
         float s = __fadd_rn(s0, s1);
         if (L > 2) {
             quant[lvl_off + (d0 >> 2)] = (int8_t)quantize_dev(s, off - 2);
-            lvl_off += R >> 2;
-            // levels 3..7 inside the warp
+            lvl_off += RB_ >> 2;
+            // relative levels 3..7 inside the warp
             const int lane = tid & 31;
 #pragma unroll
             for (int lv = 3; lv <= 7; lv++) {
@@ -312,14 +412,14 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
                     s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1 << (lv - 3)));
                     if ((lane & ((1 << (lv - 2)) - 1)) == 0)
                         quant[lvl_off + (d0 >> lv)] = (int8_t)quantize_dev(s, off - lv);
-                    lvl_off += R >> lv;
+                    lvl_off += RB_ >> lv;
                 }
             }
             if (L > 8) {
-                if (lane == 0) warp_sum[tid >> 5] = s;
+                if (lane == 0) warp_sum_s[tid >> 5] = s;
                 __syncthreads();
                 if (tid < 8) {
-                    float w = warp_sum[tid];
+                    float w = warp_sum_s[tid];
                     const size_t b0 = (size_t)blockIdx.x * 1024;
 #pragma unroll
                     for (int lv = 8; lv <= 10; lv++) {
@@ -327,29 +427,30 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
                             w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (lv - 8)));
                             if ((tid & ((1 << (lv - 7)) - 1)) == 0)
                                 quant[lvl_off + ((b0 + 128 * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
-                            lvl_off += R >> lv;
+                            lvl_off += RB_ >> lv;
                         }
                     }
-                    if (L > 11 && tid == 0) p.ptop[(size_t)frame * (R >> 10) + blockIdx.x] = w;
+                    if (L > 11 && tid == 0) p.ptop[(size_t)frame * (RB_ >> 10) + blockIdx.x] = w;
                 }
             }
         }
     }
 }
 
-// levels 11.. (only for R > 2^20 or small waterfall_size): one block per frame, pairwise tree over
-// the level-10 sums left in ptop. Tiny.
-__global__ void pyramid_tail_kernel(const PyrParams p) {
+// more than ten levels above the base (only for very deep pyramids): one block per frame, pairwise tree over
+// the sums left in ptop. Tiny.
+__global__ void pyramid_tail_kernel(const PyrParams p, int base_level) {
     const int frame = blockIdx.x;
     const size_t R = (size_t)1 << p.log2R;
-    float *buf = p.ptop + (size_t)frame * (R >> 10);
+    const int first = base_level + 11;
+    size_t n = R >> (base_level + 10);
+    float *buf = p.ptop + (size_t)frame * n;
     int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
     size_t lvl_off = 0;
-    for (int lv = 0; lv < 11; lv++) lvl_off += R >> lv;
-    size_t n = R >> 10;
-    for (int lv = 11; lv < p.levels; lv++) {
+    for (int lv = 0; lv < first; lv++) lvl_off += R >> lv;
+    for (int lv = first; lv < p.levels; lv++) {
         n >>= 1;
-        // in-place pairwise sum: element j <- buf[2j] + buf[2j+1]; done in two phases to avoid races
+        // in-place pairwise sum: element j <- buf[2j] + buf[2j+1]; read everything of a chunk before writing it
         for (size_t base = 0; base < n; base += blockDim.x) {
             size_t j = base + threadIdx.x;
             float v = 0.f;
