@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--clients", type=int, default=1024, help="demod clients per GPU")
     ap.add_argument("--ring", type=int, default=64, help="hops resident in HBM = frames per step")
     ap.add_argument("--batch", type=int, default=8, help="frames per kernel launch")
+    ap.add_argument("--banks", type=int, default=2, help="pipeline depth: clients of batch k overlap the FFT of batch k+1")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -268,7 +269,7 @@ def workload_config(cfg, args, world):
                     f"{args.clients} clients/GPU mixed AM/USB/LSB (BASELINE.json configs[1] at the metric's client count)",
         "fft_size": cfg.fft_size, "audio_fft_size": cfg.audio_fft_size, "downsample_levels": cfg.downsample_levels,
         "clients_per_gpu": args.clients, "clients_total": args.clients * world,
-        "frames_per_step": args.ring, "frames_per_launch": args.batch,
+        "frames_per_step": args.ring, "frames_per_launch": args.batch, "pipeline_banks": args.banks,
         "l2_policy": f"inputs larger than L2: {args.ring} hops x {cfg.hop_floats * 4 / 2**20:g} MiB resident ring, "
                      "each hop read by two consecutive frames only",
         "parallelism": "single GPU" if world == 1 else
@@ -301,6 +302,7 @@ def run_b200(args):
     eng.plan_r2c() if cfg.is_real else eng.plan_c2c()
     eng.set_hop_ring(H)
     eng.set_batch_frames(F)
+    eng.set_pipeline(args.banks)
     eng.clients_create(args.clients, n, cfg.audio_sps)
     for i, c in enumerate(client_table(cfg, args.clients, rank)):
         eng.client_open(i, c.l, c.mid, c.r, c.mode)
@@ -309,22 +311,32 @@ def run_b200(args):
     eng.set_stream(stream.cuda_stream)
 
     ring_t = torch.as_tensor(eng.device_hop_ring(H), device=dev)
-    spec_t = torch.as_tensor(eng.device_spectrum(F), device=dev)
+    spec_banks = []
+    for b in range(args.banks):
+        eng.select_bank(b)
+        spec_banks.append(torch.as_tensor(eng.device_spectrum(F), device=dev))
+    eng.select_bank(0)
     if rank == 0:
         fill_ring(torch, ring_t, cfg, seed=0x5EED + 2)
     torch.cuda.synchronize()
 
     frame_num = 0
+    batch_no = 0
 
     def step():
-        nonlocal frame_num
+        nonlocal frame_num, batch_no
         for g in range(H // F):
+            bank = batch_no % args.banks
+            eng.select_bank(bank)
             if rank == 0:
                 eng.execute_device(g * F, F)
+            else:
+                eng.bank_acquire()
             if world > 1:
-                dist.broadcast(spec_t, src=0)
+                dist.broadcast(spec_banks[bank], src=0)
             eng.clients_execute_device(frame_num, F)
             frame_num += F
+            batch_no += 1
 
     def barrier():
         if world > 1:
@@ -333,6 +345,7 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    eng.join_streams()
     barrier()
     sampler = ClockSampler(local)
     launches0 = eng.launch_count
@@ -342,6 +355,7 @@ def run_b200(args):
     ev0.record(stream)
     for _ in range(args.steps):
         step()
+    eng.join_streams()
     ev1.record(stream)
     barrier()
     sampler.stop()
@@ -393,11 +407,13 @@ def run_b200(args):
         # client kernels alone
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        eng.select_bank(0)
         a.record(stream)
         reps = 20
         for r_ in range(reps):
             eng.clients_execute_device(frame_num, F)
             frame_num += F
+        eng.join_streams()
         b.record(stream)
         torch.cuda.synchronize()
         breakdown["clients_us_per_frame"] = round(a.elapsed_time(b) * 1e3 / (reps * F), 3)
@@ -417,6 +433,9 @@ def run_b200(args):
         rs = np.random.default_rng(0x5EED + 3 + rank)
         for hb in host:
             hb[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
+        eng.join_streams()
+        eng.sync()
+        eng.select_bank(0)
         eng.set_option(OPT_HOST_MIRROR, 2)  # clients live on the GPU: only the pyramid returns to the host
         outs = eng.clients_fetch(0)
         load = eng.load_real_input if cfg.is_real else eng.load_complex_input

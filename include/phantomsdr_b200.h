@@ -144,6 +144,18 @@ int b200_set_batch_frames(b200_engine *e, int max_frames);
 int b200_execute_device_batch(b200_engine *e, size_t hop_index, int nframes);
 size_t b200_spectrum_stride(b200_engine *e);
 size_t b200_pyramid_stride(b200_engine *e);
+/* Software pipeline: `banks` (1..4, default 1) copies of the batch outputs. With banks > 1 the client
+ * kernels run on a second internal stream, so the clients of batch k overlap the forward FFT of batch
+ * k+1; the engine orders the two streams per bank with events. b200_select_bank picks the bank that the
+ * following execute_device / clients_execute_device / device_spectrum / device_quantized calls use.
+ * b200_bank_acquire makes the forward stream wait until the selected bank's previous clients are done
+ * (implicit in execute_device; call it before writing the bank yourself, e.g. a broadcast on a non-ingest
+ * rank). b200_join_streams makes the forward stream wait for all outstanding client work (e.g. before
+ * recording a timing event on it). */
+int b200_set_pipeline(b200_engine *e, int banks);
+int b200_select_bank(b200_engine *e, int bank);
+int b200_bank_acquire(b200_engine *e);
+int b200_join_streams(b200_engine *e);
 /* Wait for everything enqueued on the engine's stream. */
 int b200_sync(b200_engine *e);
 /* The engine's cudaStream_t (as void*), so callers can order their own work / events on it. */

@@ -43,6 +43,10 @@ SIGNATURES = {
     "b200_execute_device_batch": (_i, [_vp, _sz, _i]),
     "b200_spectrum_stride": (_sz, [_vp]),
     "b200_pyramid_stride": (_sz, [_vp]),
+    "b200_set_pipeline": (_i, [_vp, _i]),
+    "b200_select_bank": (_i, [_vp, _i]),
+    "b200_bank_acquire": (_i, [_vp]),
+    "b200_join_streams": (_i, [_vp]),
     "b200_sync": (_i, [_vp]),
     "b200_stream": (_vp, [_vp]),
     "b200_set_stream": (_i, [_vp, _vp]),

@@ -139,6 +139,18 @@ class B200FFT:
     def set_batch_frames(self, frames: int) -> None:
         check(self.L.b200_set_batch_frames(self.h, frames))
 
+    def set_pipeline(self, banks: int) -> None:
+        check(self.L.b200_set_pipeline(self.h, banks))
+
+    def select_bank(self, bank: int) -> None:
+        check(self.L.b200_select_bank(self.h, bank))
+
+    def bank_acquire(self) -> None:
+        check(self.L.b200_bank_acquire(self.h))
+
+    def join_streams(self) -> None:
+        check(self.L.b200_join_streams(self.h))
+
     @property
     def hop_floats(self) -> int:
         return self.L.b200_hop_floats(self.h)

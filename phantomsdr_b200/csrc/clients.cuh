@@ -320,32 +320,44 @@ __device__ __forceinline__ long long floordiv_ll(long long a, int b) {
     return q;
 }
 
-// running sum  s <- (s - old) + x  over j = 0..h-1 for one client column `ci` (lane = client), written to out.
-// old_j = state[j] for j < D, in[j - D] afterwards. Loads are grouped four iterations ahead of the two
-// dependent adds so only the adds sit on the loop-carried path.
-__device__ __forceinline__ float running_sum_serial(float s, const float *state, const float *in, float *out, int h,
-                                                    int D, int P, int ci) {
+// Shared-memory rows are [client][sample] with a pitch that is a multiple of 4 floats and == 4 (mod 32):
+// 16-byte aligned for 128-bit accesses, and conflict-free both for lanes along the sample index and for
+// lanes along the client index (quarter-warps of 128-bit accesses land on disjoint bank groups).
+__host__ __device__ inline int tail_pitch(int len) {
+    int p = (len + 3) & ~3;
+    while ((p & 31) != 4) p += 4;
+    return p;
+}
+
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void sts4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+
+// running sum  s <- (s - ext[j]) + ext[j + D]  for j = 0..h-1 (src/utils.h:80-85: sum -= q.back(); sum += val),
+// one lane per client. ext = [last D values of the previous frames | this frame]. Only the two dependent adds
+// per sample sit on the loop-carried path: operands are fetched one group ahead with 128-bit loads.
+__device__ __forceinline__ float running_sum_serial(float s, const float *ext, float *out, int h, int D) {
     int j = 0;
-    for (; j + 4 <= h; j += 4) {
-        float o[4], x[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int jj = j + u;
-            o[u] = (jj < D) ? state[jj * P + ci] : in[(jj - D) * P + ci];
-            x[u] = in[jj * P + ci];
+    if ((D & 3) == 0) {
+        float4 o = lds4(ext), x = lds4(ext + D);
+        for (; j + 4 <= h; j += 4) {
+            float4 on = o, xn = x;
+            if (j + 8 <= h) {
+                on = lds4(ext + j + 4);
+                xn = lds4(ext + j + 4 + D);
+            }
+            float4 r;
+            r.x = s = __fadd_rn(__fadd_rn(s, -o.x), x.x);
+            r.y = s = __fadd_rn(__fadd_rn(s, -o.y), x.y);
+            r.z = s = __fadd_rn(__fadd_rn(s, -o.z), x.z);
+            r.w = s = __fadd_rn(__fadd_rn(s, -o.w), x.w);
+            sts4(out + j, r);
+            o = on;
+            x = xn;
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            s = __fadd_rn(__fadd_rn(s, -o[u]), x[u]);
-            o[u] = s;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) out[(j + u) * P + ci] = o[u];
     }
     for (; j < h; j++) {
-        const float o = (j < D) ? state[j * P + ci] : in[(j - D) * P + ci];
-        s = __fadd_rn(__fadd_rn(s, -o), in[j * P + ci]);
-        out[j * P + ci] = s;
+        s = __fadd_rn(__fadd_rn(s, -ext[j]), ext[j + D]);
+        out[j] = s;
     }
     return s;
 }
@@ -354,16 +366,15 @@ __device__ __forceinline__ float running_sum_serial(float s, const float *state,
 // consumed), 0 = runtime loops for unusually long audio frames.
 template <int KB>
 __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientArrays ca, const ClientLaunch cl) {
-    extern __shared__ float smem_t[];
+    extern __shared__ __align__(16) float smem_t[];
     const int h = ca.h, D = ca.D, L = ca.L, NC = ca.NC;
-    const int cpb = cl.cpb, P = cl.cpb + 1;
-    float *tA = smem_t;           // [h][P] audio in (DC input)
-    float *tM = tA + h * P;       // [h][P] running sum 1 -> first-stage average
-    float *tY = tM + h * P;       // [h][P] running sum 2 -> DC blocker output
-    float *tC = tY + h * P;       // [h][P] look-ahead-delayed sample -> AGC output
-    float *tP = tC + h * P;       // [h][P] window maximum over the old samples -> desired gain
-    float *tDx = tP + h * P;      // [D][P]
-    float *tDm = tDx + D * P;     // [D][P]
+    const int cpb = cl.cpb;
+    const int pX = tail_pitch(D + h), pH = tail_pitch(h);
+    float *tX = smem_t;            // [cpb][D + h]  DC input, extended by the last D inputs
+    float *tM = tX + cpb * pX;     // [cpb][D + h]  first-stage averages, extended likewise (sum, then sum / D)
+    float *tY = tM + cpb * pX;     // [cpb][h]      running sum 2 -> DC blocker output
+    float *tC = tY + cpb * pH;     // [cpb][h]      look-ahead-delayed sample -> AGC output
+    float *tP = tC + cpb * pH;     // [cpb][h]      window maximum over the old samples -> desired gain
     __shared__ int s_slot[32];
     __shared__ unsigned char s_valid[32];
     __shared__ long long s_t0[32];
@@ -421,6 +432,7 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
         for (int ci = warp; ci < cpb; ci += kTailWarps) {
             const int slot = s_slot[ci];
             if (slot < 0 || !s_valid[ci]) continue;
+            float *X = tX + ci * pX, *Mx = tM + ci * pX, *Cc = tC + ci * pH, *Pp = tP + ci * pH;
             const float *a = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
             // AGC window of output j is samples [t0+j-L+1, t0+j]. Its old part starts at chunk c0,
             // column col0 and, as j grows, walks through chunk c0 then chunk c0+1.
@@ -440,8 +452,8 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
                 m0 = fmaxf(m0, v);
                 if (c >= c0 + 2) m1 = fmaxf(m1, v);
             }
+            float ra[KB > 0 ? KB : 1], r0[KB > 0 ? KB : 1], r1[KB > 0 ? KB : 1];
             if constexpr (KB > 0) {
-                float ra[KB], r0[KB], r1[KB];
 #pragma unroll
                 for (int b = 0; b < KB; b++) {  // every global load of this client is in flight together
                     const int col = 32 * b + lane;
@@ -449,103 +461,87 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
                     r0[b] = (col < h) ? row0[col] : 0.f;
                     r1[b] = (col < h) ? row1[col] : 0.f;
                 }
-                for (int j = lane; j < D; j += 32) {
-                    tDx[j * P + ci] = ca.dc_x[(size_t)slot * D + j];
-                    tDm[j * P + ci] = ca.dc_m[(size_t)slot * D + j];
-                }
+            }
+            for (int j = lane; j < D; j += 32) {
+                X[j] = ca.dc_x[(size_t)slot * D + j];
+                Mx[j] = ca.dc_m[(size_t)slot * D + j];
+            }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-                }
+            for (int o = 16; o > 0; o >>= 1) {
+                m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            }
+            if constexpr (KB > 0) {
 #pragma unroll
                 for (int b = 0; b < KB; b++) {
                     const int col = 32 * b + lane;
-                    if (col < h) tA[col * P + ci] = ra[b];
-                }
-#pragma unroll
-                for (int rr = 0; rr < 2; rr++) {
-                    const float mfull = rr ? m1 : m0;
-                    float carry = 0.f;
-#pragma unroll
-                    for (int b = KB - 1; b >= 0; b--) {  // suffix max of |x| inside the chunk, from the end
-                        const int col = 32 * b + lane;
-                        const float xv = rr ? r1[b] : r0[b];
-                        float m = fabsf(xv);
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const float other = __shfl_down_sync(0xffffffffu, m, o);
-                            if (lane + o < 32) m = fmaxf(m, other);
-                        }
-                        m = fmaxf(m, carry);
-                        const int j = rr * h + col - col0;  // output index served by (rr, col)
-                        if (col < h && j >= 0 && j < h) {
-                            tC[j * P + ci] = xv;
-                            tP[j * P + ci] = fmaxf(m, mfull);
-                        }
-                        carry = __shfl_sync(0xffffffffu, m, 0);
-                    }
+                    if (col < h) X[D + col] = ra[b];
                 }
             } else {
-                for (int j = lane; j < h; j += 32) tA[j * P + ci] = a[j];
-                for (int j = lane; j < D; j += 32) {
-                    tDx[j * P + ci] = ca.dc_x[(size_t)slot * D + j];
-                    tDm[j * P + ci] = ca.dc_m[(size_t)slot * D + j];
-                }
+                for (int j = lane; j < h; j += 32) X[D + j] = a[j];
+            }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-                }
-                for (int rr = 0; rr < 2; rr++) {
-                    const float *src = rr ? row1 : row0;
-                    const float mfull = rr ? m1 : m0;
-                    float carry = 0.f;
+            for (int rr = 0; rr < 2; rr++) {
+                const float *src = rr ? row1 : row0;
+                const float mfull = rr ? m1 : m0;
+                float carry = 0.f;
+                auto body = [&](int b, float xv) {  // suffix max of |x| inside the chunk, from the end
+                    const int col = 32 * b + lane;
+                    float m = fabsf(xv);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float other = __shfl_down_sync(0xffffffffu, m, o);
+                        if (lane + o < 32) m = fmaxf(m, other);
+                    }
+                    m = fmaxf(m, carry);
+                    const int j = rr * h + col - col0;  // output index served by (rr, col)
+                    if (col < h && j >= 0 && j < h) {
+                        Cc[j] = xv;
+                        Pp[j] = fmaxf(m, mfull);
+                    }
+                    carry = __shfl_sync(0xffffffffu, m, 0);
+                };
+                if constexpr (KB > 0) {
+#pragma unroll
+                    for (int b = KB - 1; b >= 0; b--) body(b, rr ? r1[b] : r0[b]);
+                } else {
                     for (int b = nb - 1; b >= 0; b--) {
                         const int col = 32 * b + lane;
-                        const float xv = (col < h) ? src[col] : 0.f;
-                        float m = fabsf(xv);
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const float other = __shfl_down_sync(0xffffffffu, m, o);
-                            if (lane + o < 32) m = fmaxf(m, other);
-                        }
-                        m = fmaxf(m, carry);
-                        const int j = rr * h + col - col0;
-                        if (col < h && j >= 0 && j < h) {
-                            tC[j * P + ci] = xv;
-                            tP[j * P + ci] = fmaxf(m, mfull);
-                        }
-                        carry = __shfl_sync(0xffffffffu, m, 0);
+                        body(b, (col < h) ? src[col] : 0.f);
                     }
                 }
             }
         }
         __syncthreads();
         // ---- P1 (serial): first running sum of the DC blocker, src/utils.h:80-85 ----
-        if (warp == 0 && my_slot >= 0 && s_valid[lane]) sum1 = running_sum_serial(sum1, tDx, tA, tM, h, D, P, lane);
+        if (warp == 0 && my_slot >= 0 && s_valid[lane])
+            sum1 = running_sum_serial(sum1, tX + lane * pX, tM + lane * pX + D, h, D);
         __syncthreads();
         // ---- P2 (parallel): getAverage() = sum / length ----
         for (int ci = warp; ci < cpb; ci += kTailWarps) {
             if (s_slot[ci] < 0 || !s_valid[ci]) continue;
-            for (int j = lane; j < h; j += 32) tM[j * P + ci] = __fdiv_rn(tM[j * P + ci], Df);
+            float *Mx = tM + ci * pX + D;
+            for (int j = lane; j < h; j += 32) Mx[j] = __fdiv_rn(Mx[j], Df);
         }
         __syncthreads();
         // ---- P3 (serial): second running sum ----
-        if (warp == 0 && my_slot >= 0 && s_valid[lane]) sum2 = running_sum_serial(sum2, tDm, tM, tY, h, D, P, lane);
+        if (warp == 0 && my_slot >= 0 && s_valid[lane])
+            sum2 = running_sum_serial(sum2, tM + lane * pX, tY + lane * pH, h, D);
         __syncthreads();
-        // ---- P4 (parallel): DC output y = x[delayed] - ma2 (src/utils.h:145-149), running |y| maximum,
-        //      window peak, desired gain (audioprocessing.cpp:48-52) ----
+        // ---- P4 (parallel): DC output y = x[delayed] - ma2 (src/utils.h:145-149: buffer[delay-1] is the input
+        //      of delay-1 samples ago = ext[j+1]), running |y| maximum, window peak, desired gain
+        //      (audioprocessing.cpp:48-52) ----
         for (int ci = warp; ci < cpb; ci += kTailWarps) {
             if (s_slot[ci] < 0 || !s_valid[ci]) continue;
+            const float *X = tX + ci * pX;
+            float *Y = tY + ci * pH, *Pp = tP + ci * pH;
             float carry = 0.f;
             for (int base = 0; base < h; base += 32) {
                 const int j = base + lane;
                 float y = 0.f, m = 0.f;
                 if (j < h) {
-                    const float ma2 = __fdiv_rn(tY[j * P + ci], Df);
-                    const float xd = (j + 1 < D) ? tDx[(j + 1) * P + ci] : tA[(j + 1 - D) * P + ci];
-                    y = __fsub_rn(xd, ma2);
+                    const float ma2 = __fdiv_rn(Y[j], Df);
+                    y = __fsub_rn(X[j + 1], ma2);
                     m = fabsf(y);
                 }
 #pragma unroll
@@ -555,9 +551,9 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
                 }
                 m = fmaxf(m, carry);
                 if (j < h) {
-                    tY[j * P + ci] = y;
-                    const float peak = fmaxf(tP[j * P + ci], m);
-                    tP[j * P + ci] = __fdiv_rn(ca.desired, __fadd_rn(peak, 1e-10f));
+                    Y[j] = y;
+                    const float peak = fmaxf(Pp[j], m);
+                    Pp[j] = __fdiv_rn(ca.desired, __fadd_rn(peak, 1e-10f));
                 }
                 carry = __shfl_sync(0xffffffffu, m, 31);
             }
@@ -566,37 +562,41 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
         __syncthreads();
         // ---- P5 (serial): attack/release recurrence on the gain, audioprocessing.cpp:54-63 ----
         if (warp == 0 && my_slot >= 0 && s_valid[lane]) {
-            const int ci = lane;
             const float att = ca.attack, rel = ca.release;
+            float *Cc = tC + lane * pH;
+            const float *Pp = tP + lane * pH;
             // outputs stay 0 until the look-ahead buffer is full (audioprocessing.cpp:45,64-66)
             long long first = (long long)L - 1 - t0;
             if (first < 0) first = 0;
             if (first > h) first = h;
             int j = 0;
-            for (; j < (int)first; j++) tC[j * P + ci] = 0.f;
-            for (; j + 4 <= h; j += 4) {
-                float d[4], c[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    d[u] = tP[(j + u) * P + ci];
-                    c[u] = tC[(j + u) * P + ci];
+            for (; j < (int)first; j++) Cc[j] = 0.f;
+            auto step = [&](float d, float c) {
+                const float ga = __fsub_rn(gain, __fmul_rn(att, __fsub_rn(gain, d)));
+                const float gr = __fadd_rn(gain, __fmul_rn(rel, __fsub_rn(d, gain)));
+                gain = (d < gain) ? ga : gr;
+                return __fmul_rn(c, gain);
+            };
+            for (; (j & 3) && j < h; j++) Cc[j] = step(Pp[j], Cc[j]);
+            if (j + 4 <= h) {
+                float4 d = lds4(Pp + j), c = lds4(Cc + j);
+                for (; j + 4 <= h; j += 4) {
+                    float4 dn = d, cn = c;
+                    if (j + 8 <= h) {
+                        dn = lds4(Pp + j + 4);
+                        cn = lds4(Cc + j + 4);
+                    }
+                    float4 r;
+                    r.x = step(d.x, c.x);
+                    r.y = step(d.y, c.y);
+                    r.z = step(d.z, c.z);
+                    r.w = step(d.w, c.w);
+                    sts4(Cc + j, r);
+                    d = dn;
+                    c = cn;
                 }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const float ga = __fsub_rn(gain, __fmul_rn(att, __fsub_rn(gain, d[u])));
-                    const float gr = __fadd_rn(gain, __fmul_rn(rel, __fsub_rn(d[u], gain)));
-                    gain = (d[u] < gain) ? ga : gr;
-                    c[u] = __fmul_rn(c[u], gain);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) tC[(j + u) * P + ci] = c[u];
             }
-            for (; j < h; j++) {
-                const float desired = tP[j * P + ci];
-                if (desired < gain) gain = __fsub_rn(gain, __fmul_rn(att, __fsub_rn(gain, desired)));
-                else gain = __fadd_rn(gain, __fmul_rn(rel, __fsub_rn(desired, gain)));
-                tC[j * P + ci] = __fmul_rn(tC[j * P + ci], gain);
-            }
+            for (; j < h; j++) Cc[j] = step(Pp[j], Cc[j]);
             t0 += h;
         }
         __syncthreads();
@@ -611,32 +611,23 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
                 continue;
             }
             if (lane == 0) ca.valid[(size_t)f * ca.max_clients + slot] = 1;
+            const float *X = tX + ci * pX, *Mx = tM + ci * pX, *Y = tY + ci * pH, *Cc = tC + ci * pH;
             const long long Fc = s_t0[ci] / h;
             const int row = (int)(Fc % NC);
             float *dst = ca.agc_ring + ((size_t)slot * NC + row) * h;
             for (int j = lane; j < h; j += 32) {
                 // dsp.cpp:152-165 with mult = 65536/4
-                const float x = tC[j * P + ci];
-                const float t = __fadd_rn(__fmul_rn(x, 16384.f), 32768.5f);
+                const float t = __fadd_rn(__fmul_rn(Cc[j], 16384.f), 32768.5f);
                 int v = __float2int_rz(t) - 32768;
                 v = max(min(v, 32767), -32768);
                 pcm[j] = v;
-                dst[j] = tY[j * P + ci];
+                dst[j] = Y[j];
             }
             if (lane == 0) ca.agc_cmax[(size_t)slot * NC + row] = s_pmax[ci];
-            // DC state: last D of [dc_x | audio_in] and [dc_m | ma1]
+            // DC state: the last D entries of the extended rows
             for (int j = lane; j < D; j += 32) {
-                const int src = h + j;  // index into the (D + h)-long concatenation
-                float nx, nm;
-                if (src >= D) {
-                    nx = tA[(src - D) * P + ci];
-                    nm = tM[(src - D) * P + ci];
-                } else {
-                    nx = tDx[src * P + ci];
-                    nm = tDm[src * P + ci];
-                }
-                ca.dc_x[(size_t)slot * D + j] = nx;
-                ca.dc_m[(size_t)slot * D + j] = nm;
+                ca.dc_x[(size_t)slot * D + j] = X[h + j];
+                ca.dc_m[(size_t)slot * D + j] = Mx[h + j];
             }
         }
         __syncthreads();

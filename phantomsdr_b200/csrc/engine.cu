@@ -97,8 +97,14 @@ struct b200_engine {
     int log2M = 0;
     size_t R = 0;  // fft_result_size
     SubPlan sp1{}, sp2{};
-    cudaStream_t stream = nullptr;      // the stream work is enqueued on
+    cudaStream_t stream = nullptr;      // the stream forward work is enqueued on
     cudaStream_t own_stream = nullptr;  // created by the engine
+    cudaStream_t cstream = nullptr;     // client kernels when banks > 1 (overlaps the next forward batch)
+    int banks = 1;                      // spectrum / pyramid banks (software pipeline depth)
+    int cur_bank = 0;
+    cudaEvent_t ev_fwd[4] = {};         // forward stream state at the time the bank's clients were enqueued
+    cudaEvent_t ev_cli[4] = {};         // the bank's clients have finished
+    bool cli_pending[4] = {};
 
     float *d_window = nullptr;
     float2 *d_Y = nullptr, *d_Z = nullptr, *d_spec = nullptr, *spec_bound = nullptr;
@@ -153,7 +159,11 @@ struct b200_engine {
         }
     }
     size_t hop_bytes_max() const { return hop_samples * 4; }
-    float2 *spec_ptr() const { return spec_bound ? spec_bound : d_spec; }
+    float2 *spec_ptr() const {
+        return spec_bound ? spec_bound : d_spec + (size_t)cur_bank * batch * spec_stride;
+    }
+    int8_t *quant_ptr() const { return d_quant + (size_t)cur_bank * batch * pyr_stride; }
+    cudaStream_t client_stream() const { return banks > 1 ? cstream : stream; }
 };
 
 namespace {
@@ -220,7 +230,20 @@ int dispatch_pass2(b200_engine *e, const FwdParams &p, int frames, bool fuse) {
 }
 
 // forward FFT + pyramid for `frames` consecutive frames starting at ring hop `hop0`
+int bank_acquire(b200_engine *e) {
+    // the forward stream may only overwrite a bank once the clients that read it are done
+    if (e->banks > 1 && e->cli_pending[e->cur_bank]) {
+        CU(cudaStreamWaitEvent(e->stream, e->ev_cli[e->cur_bank], 0));
+        e->cli_pending[e->cur_bank] = false;
+    }
+    return 0;
+}
+
 int run_forward(b200_engine *e, long hop0, int frames) {
+    {
+        int rc0 = bank_acquire(e);
+        if (rc0) return rc0;
+    }
     FwdParams p{};
     p.ring = e->d_ring;
     p.hop_bytes = e->hop_samples * e->format_bytes();
@@ -257,7 +280,7 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     const bool fuse = !e->is_real && e->opt_fused_pyramid;
     int base_level = 0;
     while ((1 << base_level) < e->sp2.T) base_level++;
-    p.quant = e->d_quant;
+    p.quant = e->quant_ptr();
     p.pyr_stride = e->pyr_stride;
     p.pscratch = e->d_pscratch;
     p.levels = e->levels;
@@ -273,7 +296,7 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     q.spec = spec;
     q.spec_stride = e->spec_stride;
     q.Z = e->d_Z;
-    q.quant = e->d_quant;
+    q.quant = e->quant_ptr();
     q.pyr_stride = e->pyr_stride;
     q.ptop = e->d_ptop;
     int log2R = 0;
@@ -376,10 +399,12 @@ int alloc_batch(b200_engine *e, int frames) {
     e->d_ptop = nullptr;
     CU(cudaMalloc(&e->d_Y, sizeof(float2) * e->M * frames));
     if (e->is_real) CU(cudaMalloc(&e->d_Z, sizeof(float2) * e->M * frames));
-    CU(cudaMalloc(&e->d_spec, sizeof(float2) * e->spec_stride * frames));
-    CU(cudaMemset(e->d_spec, 0, sizeof(float2) * e->spec_stride * frames));
-    CU(cudaMalloc(&e->d_quant, e->pyr_stride * frames));
-    CU(cudaMemset(e->d_quant, 0, e->pyr_stride * frames));
+    CU(cudaMalloc(&e->d_spec, sizeof(float2) * e->spec_stride * frames * e->banks));
+    CU(cudaMemset(e->d_spec, 0, sizeof(float2) * e->spec_stride * frames * e->banks));
+    CU(cudaMalloc(&e->d_quant, e->pyr_stride * frames * e->banks));
+    CU(cudaMemset(e->d_quant, 0, e->pyr_stride * frames * e->banks));
+    e->cur_bank = 0;
+    for (int b = 0; b < 4; b++) e->cli_pending[b] = false;
     CU(cudaMalloc(&e->d_ptop, sizeof(float) * std::max<size_t>(1, e->R / 1024) * frames));
     CU(cudaMalloc(&e->d_pscratch, sizeof(float) * (size_t)(e->sp1.S / e->sp2.T) * e->sp2.S * frames));
     e->batch = frames;
@@ -437,7 +462,7 @@ int launch_demod(b200_engine *e, const ClientLaunch &cl) {
         CU(cudaFuncSetAttribute(client_demod_kernel<kDemodThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
-    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, e->stream>>>(e->ca, cl);
+    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, e->client_stream()>>>(e->ca, cl);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -449,7 +474,7 @@ template <int KB> int launch_tail_kb(b200_engine *e, const ClientLaunch &cl) {
         return 0;
     }
     const int blocks = (cl.nactive + cl.cpb - 1) / cl.cpb;
-    client_tail_kernel<KB><<<blocks, kTailThreads, e->tail_smem, e->stream>>>(e->ca, cl);
+    client_tail_kernel<KB><<<blocks, kTailThreads, e->tail_smem, e->client_stream()>>>(e->ca, cl);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -479,16 +504,23 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
             return e->slots[a].r < e->slots[b].r;
         });
         CU(cudaMemcpyAsync(e->ca.slots, e->slots.data(), sizeof(ClientSlot) * e->slots.size(), cudaMemcpyHostToDevice,
-                           e->stream));
+                           e->client_stream()));
         if (!e->order.empty())
             CU(cudaMemcpyAsync(e->d_order, e->order.data(), sizeof(int) * e->order.size(), cudaMemcpyHostToDevice,
-                               e->stream));
+                               e->client_stream()));
         // pageable source: the runtime stages it before returning, so host vectors may change afterwards
         e->slots_dirty = false;
     }
     e->last_client_frames = nframes;
+    cudaStream_t cs = e->client_stream();
+    if (e->banks > 1) {
+        // everything enqueued on the forward stream so far (this bank's FFT, and any broadcast the caller
+        // put behind it) must land before the clients read the bank
+        CU(cudaEventRecord(e->ev_fwd[e->cur_bank], e->stream));
+        CU(cudaStreamWaitEvent(cs, e->ev_fwd[e->cur_bank], 0));
+    }
     // closed slots read back as invalid
-    CU(cudaMemsetAsync(e->ca.valid, 0, (size_t)e->ca.max_clients * nframes, e->stream));
+    CU(cudaMemsetAsync(e->ca.valid, 0, (size_t)e->ca.max_clients * nframes, cs));
     if (e->order.empty()) return 0;
     ClientLaunch cl{};
     cl.spec = e->spec_ptr();
@@ -504,6 +536,10 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     if (rc) return rc;
     rc = launch_tail(e, cl);
     if (rc) return rc;
+    if (e->banks > 1) {
+        CU(cudaEventRecord(e->ev_cli[e->cur_bank], cs));
+        e->cli_pending[e->cur_bank] = true;
+    }
     // one-shot reset flags have been consumed by this launch
     bool any = false;
     for (auto &s : e->slots)
@@ -592,6 +628,14 @@ void b200_engine_destroy(b200_engine *e) {
         if (p) cudaFree(p);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_quant) cudaFreeHost(e->h_quant);
+    if (e->cstream) {
+        cudaStreamSynchronize(e->cstream);
+        for (int b = 0; b < 4; b++) {
+            if (e->ev_fwd[b]) cudaEventDestroy(e->ev_fwd[b]);
+            if (e->ev_cli[b]) cudaEventDestroy(e->ev_cli[b]);
+        }
+        cudaStreamDestroy(e->cstream);
+    }
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -698,13 +742,13 @@ int b200_execute(b200_engine *e) {
         CU(cudaMemcpyAsync(e->h_out, e->spec_ptr(), sizeof(float2) * bins, cudaMemcpyDeviceToHost, e->stream));
     }
     if (e->opt_mirror & 2)
-        CU(cudaMemcpyAsync(e->h_quant, e->d_quant, e->pyr_bytes, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(e->h_quant, e->quant_ptr(), e->pyr_bytes, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return 0;
 }
 
 void *b200_device_spectrum(b200_engine *e) { return e ? e->spec_ptr() : nullptr; }
-void *b200_device_quantized(b200_engine *e) { return e ? e->d_quant : nullptr; }
+void *b200_device_quantized(b200_engine *e) { return e ? e->quant_ptr() : nullptr; }
 void *b200_device_hop_ring(b200_engine *e) { return e ? e->d_ring : nullptr; }
 size_t b200_hop_floats(b200_engine *e) { return e ? e->hop_samples : 0; }
 size_t b200_spectrum_bins(b200_engine *e) {
@@ -746,6 +790,44 @@ int b200_sync(b200_engine *e) {
     if (!e) return fail(B200_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
+    if (e->cstream) CU(cudaStreamSynchronize(e->cstream));
+    return 0;
+}
+int b200_set_pipeline(b200_engine *e, int banks) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->planned) return fail(B200_ESTATE, "set_pipeline before plan");
+    if (banks < 1 || banks > 4) return fail(B200_EINVAL, "banks must be 1..4");
+    if (e->spec_bound) return fail(B200_ESTATE, "spectrum is bound to an external buffer");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->cstream) CU(cudaStreamSynchronize(e->cstream));
+    if (banks > 1 && !e->cstream) {
+        CU(cudaStreamCreateWithFlags(&e->cstream, cudaStreamNonBlocking));
+        for (int b = 0; b < 4; b++) {
+            CU(cudaEventCreateWithFlags(&e->ev_fwd[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e->ev_cli[b], cudaEventDisableTiming));
+        }
+    }
+    e->banks = banks;
+    return alloc_batch(e, e->batch);
+}
+int b200_select_bank(b200_engine *e, int bank) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (bank < 0 || bank >= e->banks) return fail(B200_EINVAL, "bank %d outside 0..%d", bank, e->banks - 1);
+    e->cur_bank = bank;
+    return 0;
+}
+int b200_bank_acquire(b200_engine *e) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    return bank_acquire(e);
+}
+int b200_join_streams(b200_engine *e) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (e->banks > 1)
+        for (int b = 0; b < e->banks; b++)
+            if (e->cli_pending[b]) CU(cudaStreamWaitEvent(e->stream, e->ev_cli[b], 0));
     return 0;
 }
 void *b200_stream(b200_engine *e) { return e ? (void *)e->stream : nullptr; }
@@ -865,7 +947,9 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     // launch geometry
     if (sizeof(float2) * 2 * ca.n > 200 * 1024) return fail(B200_ENOTSUP, "audio_fft_size %d too large", ca.n);
     e->tail_cpb = kTailMaxCpb;
-    auto tail_bytes = [&](int cpb) { return sizeof(float) * (size_t)(5 * ca.h + 2 * ca.D) * (cpb + 1); };
+    auto tail_bytes = [&](int cpb) {
+        return sizeof(float) * (size_t)cpb * (2 * (size_t)tail_pitch(ca.D + ca.h) + 3 * (size_t)tail_pitch(ca.h));
+    };
     while (e->tail_cpb > 1 && tail_bytes(e->tail_cpb) > 200 * 1024) e->tail_cpb /= 2;
     if (tail_bytes(e->tail_cpb) > 200 * 1024) return fail(B200_ENOTSUP, "audio_fft_size %d too large for the tail kernel", ca.n);
     e->tail_smem = tail_bytes(e->tail_cpb);
@@ -953,14 +1037,12 @@ int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_o
     if (frame < 0 || frame >= e->batch) return fail(B200_EINVAL, "frame %d outside batch", frame);
     CU(cudaSetDevice(e->device));
     const size_t mc = e->ca.max_clients, h = e->ca.h;
+    cudaStream_t cs = e->client_stream();
     if (pcm_out)
-        CU(cudaMemcpyAsync(pcm_out, e->ca.pcm + (size_t)frame * mc * h, sizeof(int32_t) * mc * h, cudaMemcpyDeviceToHost,
-                           e->stream));
-    if (pwr_out)
-        CU(cudaMemcpyAsync(pwr_out, e->ca.pwr + (size_t)frame * mc, sizeof(float) * mc, cudaMemcpyDeviceToHost, e->stream));
-    if (valid_out)
-        CU(cudaMemcpyAsync(valid_out, e->ca.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpyAsync(pcm_out, e->ca.pcm + (size_t)frame * mc * h, sizeof(int32_t) * mc * h, cudaMemcpyDeviceToHost, cs));
+    if (pwr_out) CU(cudaMemcpyAsync(pwr_out, e->ca.pwr + (size_t)frame * mc, sizeof(float) * mc, cudaMemcpyDeviceToHost, cs));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, e->ca.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     return 0;
 }
 
@@ -980,8 +1062,8 @@ int b200_clients_read_pre_dc(b200_engine *e, float *out) {
     if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
     CU(cudaSetDevice(e->device));
     CU(cudaMemcpyAsync(out, e->ca.audio_pre, sizeof(float) * (size_t)e->ca.max_clients * e->ca.h, cudaMemcpyDeviceToHost,
-                       e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+                       e->client_stream()));
+    CU(cudaStreamSynchronize(e->client_stream()));
     return 0;
 }
 
@@ -1021,7 +1103,7 @@ int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const 
     CU(cudaMemcpyAsync(d_src, src.data(), sizeof(size_t) * nclients, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d_dst, dst.data(), sizeof(size_t) * nclients, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(d_len, len.data(), sizeof(int) * nclients, cudaMemcpyHostToDevice, e->stream));
-    waterfall_gather_kernel<<<nclients, 256, 0, e->stream>>>(e->d_quant, d_src, d_len, d_dst, d_out);
+    waterfall_gather_kernel<<<nclients, 256, 0, e->stream>>>(e->quant_ptr(), d_src, d_len, d_dst, d_out);
     e->launches++;
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaMemcpyAsync(staged.data(), d_out, staged.size(), cudaMemcpyDeviceToHost, e->stream);
