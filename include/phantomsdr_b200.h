@@ -229,6 +229,9 @@ int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const 
 
 /* Kernel-launch counter since creation (for bench.py's gpu_launches). */
 uint64_t b200_launch_count(b200_engine *e);
+/* Profiling aid: accumulate the SM-clock cycles block 0 of the client tail kernel spends in each of its
+ * seven phases (load, sum1, avg, sum2, peak, gain, store). out (nullable) receives the totals so far. */
+int b200_debug_tail_profile(b200_engine *e, int enable, long long out[8]);
 
 #ifdef __cplusplus
 }

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b200_clients_read_pre_dc": (_i, [_vp, _vp]),
     "b200_waterfall_gather": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200_launch_count": (_u64, [_vp]),
+    "b200_debug_tail_profile": (_i, [_vp, _i, _vp]),
 }
 
 _lib = None

@@ -68,7 +68,8 @@ struct ClientLaunch {
     int is_real;
     const int *order;    // active slots in (l, r) order
     int nactive;
-    int cpb;             // tail kernel: clients per block (<= 32), tiles are [j][cpb + 1]
+    int cpb;             // tail kernel: clients per block
+    long long *prof;     // optional: per-phase SM clock totals of block 0 (profiling aid), 8 entries
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -338,22 +339,32 @@ __device__ __forceinline__ void sts4(float *p, float4 v) { *reinterpret_cast<flo
 __device__ __forceinline__ float running_sum_serial(float s, const float *ext, float *out, int h, int D) {
     int j = 0;
     if ((D & 3) == 0) {
-        float4 o = lds4(ext), x = lds4(ext + D);
-        for (; j + 4 <= h; j += 4) {
-            float4 on = o, xn = x;
-            if (j + 8 <= h) {
-                on = lds4(ext + j + 4);
-                xn = lds4(ext + j + 4 + D);
+#define RS4(OO, XX, dst)                                    \
+    {                                                       \
+        float4 r;                                           \
+        r.x = s = __fadd_rn(__fadd_rn(s, -OO.x), XX.x);     \
+        r.y = s = __fadd_rn(__fadd_rn(s, -OO.y), XX.y);     \
+        r.z = s = __fadd_rn(__fadd_rn(s, -OO.z), XX.z);     \
+        r.w = s = __fadd_rn(__fadd_rn(s, -OO.w), XX.w);     \
+        sts4(dst, r);                                       \
+    }
+        if (h >= 8) {
+            float4 o0 = lds4(ext), x0 = lds4(ext + D);
+            for (; j + 8 <= h; j += 8) {
+                const float4 o1 = lds4(ext + j + 4), x1 = lds4(ext + j + 4 + D);
+                RS4(o0, x0, out + j)
+                if (j + 12 <= h) {  // operands of the next group, fetched while this one's adds retire
+                    o0 = lds4(ext + j + 8);
+                    x0 = lds4(ext + j + 8 + D);
+                }
+                RS4(o1, x1, out + j + 4)
             }
-            float4 r;
-            r.x = s = __fadd_rn(__fadd_rn(s, -o.x), x.x);
-            r.y = s = __fadd_rn(__fadd_rn(s, -o.y), x.y);
-            r.z = s = __fadd_rn(__fadd_rn(s, -o.z), x.z);
-            r.w = s = __fadd_rn(__fadd_rn(s, -o.w), x.w);
-            sts4(out + j, r);
-            o = on;
-            x = xn;
         }
+        for (; j + 4 <= h; j += 4) {
+            const float4 o = lds4(ext + j), x = lds4(ext + j + D);
+            RS4(o, x, out + j)
+        }
+#undef RS4
     }
     for (; j < h; j++) {
         s = __fadd_rn(__fadd_rn(s, -ext[j]), ext[j + D]);
@@ -421,13 +432,21 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
     __syncthreads();
 
     const float Df = (float)D;
-    const int nb = (KB > 0) ? KB : (h + 31) / 32;
+    long long tprev = 0;
+    const bool profiling = cl.prof != nullptr && blockIdx.x == 0 && tid == 0;
+#define TAIL_PHASE(k)                              \
+    if (profiling) {                               \
+        const long long tn = clock64();            \
+        cl.prof[k] += tn - tprev;                  \
+        tprev = tn;                                \
+    }
     for (int f = 0; f < cl.nframes; f++) {
         if (warp == 0) {
             s_valid[lane] = (my_slot >= 0) ? ca.valid_a[(size_t)f * ca.max_clients + my_slot] : 0;
             s_t0[lane] = t0;
         }
         __syncthreads();
+        if (profiling) tprev = clock64();
         // ---- P0: loads, lanes along j. Old-sample window maxima and delayed samples. ----
         for (int ci = warp; ci < cpb; ci += kTailWarps) {
             const int slot = s_slot[ci];
@@ -480,54 +499,98 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
             } else {
                 for (int j = lane; j < h; j += 32) X[D + j] = a[j];
             }
+            // The two old chunks go to shared memory (rows that are still free at this point), then each lane
+            // owns a contiguous segment: local suffix max, one warp scan over the 32 segment maxima, fold back.
+            float *R0 = tY + ci * pH, *R1 = tM + ci * pX + D;
+            if constexpr (KB > 0) {
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const float *src = rr ? row1 : row0;
-                const float mfull = rr ? m1 : m0;
-                float carry = 0.f;
-                auto body = [&](int b, float xv) {  // suffix max of |x| inside the chunk, from the end
+                for (int b = 0; b < KB; b++) {
                     const int col = 32 * b + lane;
-                    float m = fabsf(xv);
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const float other = __shfl_down_sync(0xffffffffu, m, o);
-                        if (lane + o < 32) m = fmaxf(m, other);
+                    if (col < h) {
+                        R0[col] = r0[b];
+                        R1[col] = r1[b];
                     }
-                    m = fmaxf(m, carry);
-                    const int j = rr * h + col - col0;  // output index served by (rr, col)
-                    if (col < h && j >= 0 && j < h) {
-                        Cc[j] = xv;
-                        Pp[j] = fmaxf(m, mfull);
-                    }
-                    carry = __shfl_sync(0xffffffffu, m, 0);
-                };
-                if constexpr (KB > 0) {
+                }
+            } else {
+                for (int col = lane; col < h; col += 32) {
+                    R0[col] = row0[col];
+                    R1[col] = row1[col];
+                }
+            }
+            __syncwarp();
+            constexpr bool kStatic = KB > 0;
+            const int seg = kStatic ? KB : (h + 31) / 32;
+            const int s0 = lane * seg;
+            float run0 = 0.f, run1 = 0.f;
 #pragma unroll
-                    for (int b = KB - 1; b >= 0; b--) body(b, rr ? r1[b] : r0[b]);
-                } else {
-                    for (int b = nb - 1; b >= 0; b--) {
-                        const int col = 32 * b + lane;
-                        body(b, (col < h) ? src[col] : 0.f);
+            for (int u = (kStatic ? KB : seg) - 1; u >= 0; u--) {
+                const int col = s0 + u;
+                if (col < h) {
+                    run0 = fmaxf(run0, fabsf(R0[col]));
+                    run1 = fmaxf(run1, fabsf(R1[col]));
+                }
+            }
+            float in0 = run0, in1 = run1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {  // inclusive suffix max over lanes
+                const float a0 = __shfl_down_sync(0xffffffffu, in0, o);
+                const float a1 = __shfl_down_sync(0xffffffffu, in1, o);
+                if (lane + o < 32) {
+                    in0 = fmaxf(in0, a0);
+                    in1 = fmaxf(in1, a1);
+                }
+            }
+            run0 = __shfl_down_sync(0xffffffffu, in0, 1);
+            run1 = __shfl_down_sync(0xffffffffu, in1, 1);
+            if (lane == 31) run0 = run1 = 0.f;
+#pragma unroll
+            for (int u = (kStatic ? KB : seg) - 1; u >= 0; u--) {
+                const int col = s0 + u;
+                if (col < h) {
+                    const float x0 = R0[col], x1 = R1[col];
+                    run0 = fmaxf(run0, fabsf(x0));
+                    run1 = fmaxf(run1, fabsf(x1));
+                    const int ja = col - col0;      // output index served by (chunk c0, col)
+                    const int jb = h + col - col0;  // ... by (chunk c0+1, col)
+                    if (ja >= 0) {                  // ja < h always
+                        Cc[ja] = x0;
+                        Pp[ja] = fmaxf(run0, m0);
+                    }
+                    if (jb < h) {                   // jb >= 0 always
+                        Cc[jb] = x1;
+                        Pp[jb] = fmaxf(run1, m1);
                     }
                 }
             }
         }
         __syncthreads();
+        TAIL_PHASE(0)
         // ---- P1 (serial): first running sum of the DC blocker, src/utils.h:80-85 ----
         if (warp == 0 && my_slot >= 0 && s_valid[lane])
             sum1 = running_sum_serial(sum1, tX + lane * pX, tM + lane * pX + D, h, D);
         __syncthreads();
+        TAIL_PHASE(1)
         // ---- P2 (parallel): getAverage() = sum / length ----
         for (int ci = warp; ci < cpb; ci += kTailWarps) {
             if (s_slot[ci] < 0 || !s_valid[ci]) continue;
             float *Mx = tM + ci * pX + D;
-            for (int j = lane; j < h; j += 32) Mx[j] = __fdiv_rn(Mx[j], Df);
+            if constexpr (KB > 0) {
+#pragma unroll
+                for (int b = 0; b < KB; b++) {
+                    const int j = 32 * b + lane;
+                    if (j < h) Mx[j] = __fdiv_rn(Mx[j], Df);
+                }
+            } else {
+                for (int j = lane; j < h; j += 32) Mx[j] = __fdiv_rn(Mx[j], Df);
+            }
         }
         __syncthreads();
+        TAIL_PHASE(2)
         // ---- P3 (serial): second running sum ----
         if (warp == 0 && my_slot >= 0 && s_valid[lane])
             sum2 = running_sum_serial(sum2, tM + lane * pX, tY + lane * pH, h, D);
         __syncthreads();
+        TAIL_PHASE(3)
         // ---- P4 (parallel): DC output y = x[delayed] - ma2 (src/utils.h:145-149: buffer[delay-1] is the input
         //      of delay-1 samples ago = ext[j+1]), running |y| maximum, window peak, desired gain
         //      (audioprocessing.cpp:48-52) ----
@@ -535,31 +598,44 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
             if (s_slot[ci] < 0 || !s_valid[ci]) continue;
             const float *X = tX + ci * pX;
             float *Y = tY + ci * pH, *Pp = tP + ci * pH;
-            float carry = 0.f;
-            for (int base = 0; base < h; base += 32) {
-                const int j = base + lane;
-                float y = 0.f, m = 0.f;
-                if (j < h) {
-                    const float ma2 = __fdiv_rn(Y[j], Df);
-                    y = __fsub_rn(X[j + 1], ma2);
-                    m = fabsf(y);
-                }
+            // lane owns the contiguous samples [lane*seg, lane*seg + seg): local running max, one warp scan of
+            // the 32 segment maxima, then the exclusive prefix is folded back in
+            constexpr bool kStatic = KB > 0;
+            const int seg = kStatic ? KB : (h + 31) / 32;
+            const int j0 = lane * seg;
+            float run = 0.f;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {  // inclusive prefix max
-                    const float other = __shfl_up_sync(0xffffffffu, m, o);
-                    if (lane >= o) m = fmaxf(m, other);
-                }
-                m = fmaxf(m, carry);
+            for (int u = 0; u < (kStatic ? KB : seg); u++) {
+                const int j = j0 + u;
                 if (j < h) {
+                    const float y = __fsub_rn(X[j + 1], __fdiv_rn(Y[j], Df));
                     Y[j] = y;
-                    const float peak = fmaxf(Pp[j], m);
+                    run = fmaxf(run, fabsf(y));
+                }
+            }
+            float incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float other = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = fmaxf(incl, other);
+            }
+            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0.f;
+            run = excl;
+#pragma unroll
+            for (int u = 0; u < (kStatic ? KB : seg); u++) {
+                const int j = j0 + u;
+                if (j < h) {
+                    run = fmaxf(run, fabsf(Y[j]));
+                    const float peak = fmaxf(Pp[j], run);
                     Pp[j] = __fdiv_rn(ca.desired, __fadd_rn(peak, 1e-10f));
                 }
-                carry = __shfl_sync(0xffffffffu, m, 31);
             }
+            const float carry = __shfl_sync(0xffffffffu, incl, 31);
             if (lane == 0) s_pmax[ci] = carry;
         }
         __syncthreads();
+        TAIL_PHASE(4)
         // ---- P5 (serial): attack/release recurrence on the gain, audioprocessing.cpp:54-63 ----
         if (warp == 0 && my_slot >= 0 && s_valid[lane]) {
             const float att = ca.attack, rel = ca.release;
@@ -570,36 +646,48 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
             if (first < 0) first = 0;
             if (first > h) first = h;
             int j = 0;
-            for (; j < (int)first; j++) Cc[j] = 0.f;
-            auto step = [&](float d, float c) {
-                const float ga = __fsub_rn(gain, __fmul_rn(att, __fsub_rn(gain, d)));
-                const float gr = __fadd_rn(gain, __fmul_rn(rel, __fsub_rn(d, gain)));
-                gain = (d < gain) ? ga : gr;
-                return __fmul_rn(c, gain);
+            for (; j < (int)first; j++) Cc[j] = 0.f;  // AGC output is 0 until the buffer is full ...
+            // gain -= attack*(gain-desired) if desired < gain, else gain += release*(desired-gain)
+            // (audioprocessing.cpp:54-60). With t = gain - desired both arms are gain - c*t (negation and the
+            // sign-symmetric product are exact), and because attack >= release > 0 the arm is picked by
+            // max(attack*t, release*t): no predicate on the loop-carried path.
+            auto step = [&](float d) {
+                const float t = __fsub_rn(gain, d);
+                gain = __fsub_rn(gain, fmaxf(__fmul_rn(att, t), __fmul_rn(rel, t)));
+                return gain;
             };
-            for (; (j & 3) && j < h; j++) Cc[j] = step(Pp[j], Cc[j]);
-            if (j + 4 <= h) {
-                float4 d = lds4(Pp + j), c = lds4(Cc + j);
-                for (; j + 4 <= h; j += 4) {
-                    float4 dn = d, cn = c;
-                    if (j + 8 <= h) {
-                        dn = lds4(Pp + j + 4);
-                        cn = lds4(Cc + j + 4);
-                    }
-                    float4 r;
-                    r.x = step(d.x, c.x);
-                    r.y = step(d.y, c.y);
-                    r.z = step(d.z, c.z);
-                    r.w = step(d.w, c.w);
-                    sts4(Cc + j, r);
-                    d = dn;
-                    c = cn;
+#define G4(DD, dst)              \
+    {                            \
+        float4 r;                \
+        r.x = step(DD.x);        \
+        r.y = step(DD.y);        \
+        r.z = step(DD.z);        \
+        r.w = step(DD.w);        \
+        sts4(dst, r);            \
+    }
+            // the gain sequence overwrites the desired-gain row; the product with the delayed sample is
+            // formed in the parallel store phase
+            float *Gg = tP + lane * pH;
+            for (; (j & 3) && j < h; j++) Gg[j] = step(Pp[j]);
+            if (j + 8 <= h) {
+                float4 d0 = lds4(Pp + j);
+                for (; j + 8 <= h; j += 8) {
+                    const float4 d1 = lds4(Pp + j + 4);
+                    G4(d0, Gg + j)
+                    if (j + 12 <= h) d0 = lds4(Pp + j + 8);
+                    G4(d1, Gg + j + 4)
                 }
             }
-            for (; j < h; j++) Cc[j] = step(Pp[j], Cc[j]);
+            for (; j + 4 <= h; j += 4) {
+                const float4 d = lds4(Pp + j);
+                G4(d, Gg + j)
+            }
+#undef G4
+            for (; j < h; j++) Gg[j] = step(Pp[j]);
             t0 += h;
         }
         __syncthreads();
+        TAIL_PHASE(5)
         // ---- P6 (parallel): write back ----
         for (int ci = warp; ci < cpb; ci += kTailWarps) {
             const int slot = s_slot[ci];
@@ -611,17 +699,20 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
                 continue;
             }
             if (lane == 0) ca.valid[(size_t)f * ca.max_clients + slot] = 1;
-            const float *X = tX + ci * pX, *Mx = tM + ci * pX, *Y = tY + ci * pH, *Cc = tC + ci * pH;
+            const float *X = tX + ci * pX, *Mx = tM + ci * pX, *Y = tY + ci * pH, *Cc = tC + ci * pH, *Gg = tP + ci * pH;
             const long long Fc = s_t0[ci] / h;
             const int row = (int)(Fc % NC);
             float *dst = ca.agc_ring + ((size_t)slot * NC + row) * h;
-            for (int j = lane; j < h; j += 32) {
-                // dsp.cpp:152-165 with mult = 65536/4
-                const float t = __fadd_rn(__fmul_rn(Cc[j], 16384.f), 32768.5f);
-                int v = __float2int_rz(t) - 32768;
-                v = max(min(v, 32767), -32768);
-                pcm[j] = v;
-                dst[j] = Y[j];
+#pragma unroll
+            for (int b = 0; b < (KB > 0 ? KB : 1); b++) {
+                for (int j = 32 * b + lane; j < h; j += (KB > 0 ? h : 32)) {
+                    // dsp.cpp:152-165 with mult = 65536/4
+                    const float t = __fadd_rn(__fmul_rn(__fmul_rn(Cc[j], Gg[j]), 16384.f), 32768.5f);
+                    int v = __float2int_rz(t) - 32768;
+                    v = max(min(v, 32767), -32768);
+                    pcm[j] = v;
+                    dst[j] = Y[j];
+                }
             }
             if (lane == 0) ca.agc_cmax[(size_t)slot * NC + row] = s_pmax[ci];
             // DC state: the last D entries of the extended rows
@@ -631,7 +722,9 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
             }
         }
         __syncthreads();
+        TAIL_PHASE(6)
     }
+#undef TAIL_PHASE
     if (warp == 0 && my_slot >= 0) {
         ca.agc_gain[my_slot] = gain;
         ca.agc_t0[my_slot] = t0;

@@ -146,6 +146,7 @@ struct b200_engine {
     int tail_cpb = 32;
     size_t tail_smem = 0;
     int last_client_frames = 0;
+    long long *d_prof = nullptr;
 
     uint64_t launches = 0;
 
@@ -532,6 +533,7 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     cl.order = e->d_order;
     cl.nactive = (int)e->order.size();
     cl.cpb = e->tail_cpb;
+    cl.prof = e->d_prof;
     int rc = launch_demod(e, cl);
     if (rc) return rc;
     rc = launch_tail(e, cl);
@@ -1119,6 +1121,24 @@ int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const 
 }
 
 uint64_t b200_launch_count(b200_engine *e) { return e ? e->launches : 0; }
+
+int b200_debug_tail_profile(b200_engine *e, int enable, long long out[8]) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    CU(cudaSetDevice(e->device));
+    if (e->d_prof && out) {
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(out, e->d_prof, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+    }
+    if (enable && !e->d_prof) {
+        CU(cudaMalloc(&e->d_prof, sizeof(long long) * 8));
+    }
+    if (e->d_prof) CU(cudaMemset(e->d_prof, 0, sizeof(long long) * 8));
+    if (!enable && e->d_prof) {
+        cudaFree(e->d_prof);
+        e->d_prof = nullptr;
+    }
+    return 0;
+}
 
 }  // extern "C"
 #pragma GCC visibility pop
