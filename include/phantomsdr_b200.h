@@ -111,7 +111,10 @@ int b200_execute(b200_engine *e);
 #define B200_OPT_RELOAD_BOTH 1   /* 0 (default) / 1 */
 #define B200_OPT_HOST_MIRROR 2   /* bitmask: 1 = spectrum, 2 = pyramid; default 3 */
 #define B200_OPT_INPUT_FORMAT 3  /* B200_FMT_*: format of the halves given to b200_load_raw_input */
-#define B200_OPT_FUSED_PYRAMID 5 /* 1 (default): waterfall levels 0..log2(T)-1 come straight out of FFT pass 2 */
+#define B200_OPT_FUSED_PYRAMID 5 /* waterfall source: 1 (default) = |X|^2, log and levels 0..log2(T)-1 straight out of FFT pass 2's
+                                   registers, upper levels in a small kernel; 2 = pass 2 stores |X|^2, quantiser + pyramid in
+                                   one streaming kernel; 0 = the pyramid kernel re-reads the spectrum */
+#define B200_OPT_TMA 6           /* 1 (default): persistent TMA-fed FFT passes where available (2^20-point transforms) */
 #define B200_OPT_STAGE_MASK 4    /* profiling aid: bit0 = FFT pass 1, bit1 = pass 2, bit2 = pyramid; default 7 */
 int b200_set_option(b200_engine *e, int option, int value);
 

@@ -17,6 +17,7 @@
 #include "../../include/phantomsdr_b200.h"
 #include "clients.cuh"
 #include "fft_fwd.cuh"
+#include "fft_tma.cuh"
 
 using namespace b200;
 
@@ -47,6 +48,7 @@ SubPlan sub_plan(int S, const char *tile_env) {
     int t1024 = 16;
     if (const char *v = getenv(tile_env)) {  // tuning aid: B200_TILE1 / B200_TILE2 = 8 | 16 for the 1024-point passes
         if (atoi(v) == 8) t1024 = 8;
+        if (atoi(v) == 4) t1024 = 4;
     }
     switch (S) {
     case 256: return {256, 16, 16, 32};
@@ -131,6 +133,10 @@ struct b200_engine {
     int opt_mirror = 3;
     int opt_stage_mask = 7;
     int opt_fused_pyramid = 1;
+    int opt_tma = 1;
+    bool tma_ok = false;
+    int num_sms = 148;
+    CUtensorMap ring_map{}, window_map{};
 
     int npeers = 0;
     float2 *peers[kMaxPeers] = {};
@@ -169,25 +175,33 @@ struct b200_engine {
 
 namespace {
 
-template <int RA, int RB, int T, bool RAW> int launch_pass1(b200_engine *e, const FwdParams &p, int frames) {
+template <int RA, int RB, int T, bool RAW, bool REAL> int launch_pass1r(b200_engine *e, const FwdParams &p, int frames) {
     constexpr int threads = T * CMax<RA, RB>::v;
     constexpr int PAD = (T < 16) ? (16 - T) : 0;
     constexpr size_t smem = sizeof(float2) * RB * (RA * T + PAD);
     if (frames == 0) {  // preparation call from plan time
-        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T, RAW, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
         return 0;
     }
     dim3 grid(p.N2 / T, frames);
-    fft_pass1_kernel<RA, RB, T, RAW><<<grid, threads, smem, e->stream>>>(p);
+    fft_pass1_kernel<RA, RB, T, RAW, REAL><<<grid, threads, smem, e->stream>>>(p);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
 }
+template <int RA, int RB, int T, bool RAW> int launch_pass1(b200_engine *e, const FwdParams &p, int frames) {
+    if (frames == 0) {
+        int rc = launch_pass1r<RA, RB, T, RAW, false>(e, p, 0);
+        return rc ? rc : launch_pass1r<RA, RB, T, RAW, true>(e, p, 0);
+    }
+    return p.is_real ? launch_pass1r<RA, RB, T, RAW, true>(e, p, frames) : launch_pass1r<RA, RB, T, RAW, false>(e, p, frames);
+}
 
-template <int RA, int RB, int T, bool FUSE> int launch_pass2(b200_engine *e, const FwdParams &p, int frames) {
+template <int RA, int RB, int T, int FUSE> int launch_pass2(b200_engine *e, const FwdParams &p, int frames) {
     constexpr int threads = T * CMax<RA, RB>::v;
     constexpr size_t smem = sizeof(float2) * RB * (RA * T + 1);
-    static_assert(!FUSE || sizeof(float) * RA * RB * (T + 4) <= smem, "power tile must fit in the exchange buffer");
+    static_assert(FUSE != 1 || sizeof(float) * RA * RB * (T + 4) <= smem, "power tile must fit in the exchange buffer");
     if (frames == 0) {  // preparation call from plan time
         CU(cudaFuncSetAttribute(fft_pass2_kernel<RA, RB, T, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
@@ -205,6 +219,7 @@ template <bool RAW> int dispatch_pass1_fmt(b200_engine *e, const FwdParams &p, i
     if (sp.S == 512) return launch_pass1<16, 32, 16, RAW>(e, p, frames);
     if (sp.S == 1024 && sp.T == 16) return launch_pass1<32, 32, 16, RAW>(e, p, frames);
     if (sp.S == 1024 && sp.T == 8) return launch_pass1<32, 32, 8, RAW>(e, p, frames);
+    if (sp.S == 1024 && sp.T == 4) return launch_pass1<32, 32, 4, RAW>(e, p, frames);
     return fail(B200_ENOTSUP, "no pass-1 kernel for sub-transform %d", sp.S);
 }
 int dispatch_pass1(b200_engine *e, const FwdParams &p, int frames) {
@@ -214,23 +229,107 @@ int dispatch_pass1(b200_engine *e, const FwdParams &p, int frames) {
     }
     return p.in_format == FMT_F32 ? dispatch_pass1_fmt<false>(e, p, frames) : dispatch_pass1_fmt<true>(e, p, frames);
 }
-template <bool FUSE> int dispatch_pass2_f(b200_engine *e, const FwdParams &p, int frames) {
+template <int FUSE> int dispatch_pass2_f(b200_engine *e, const FwdParams &p, int frames) {
     const SubPlan &sp = e->sp2;
     if (sp.S == 256) return launch_pass2<16, 16, 32, FUSE>(e, p, frames);
     if (sp.S == 512) return launch_pass2<16, 32, 16, FUSE>(e, p, frames);
     if (sp.S == 1024 && sp.T == 16) return launch_pass2<32, 32, 16, FUSE>(e, p, frames);
     if (sp.S == 1024 && sp.T == 8) return launch_pass2<32, 32, 8, FUSE>(e, p, frames);
+    if (sp.S == 1024 && sp.T == 4) return launch_pass2<32, 32, 4, FUSE>(e, p, frames);
     return fail(B200_ENOTSUP, "no pass-2 kernel for sub-transform %d", sp.S);
 }
-int dispatch_pass2(b200_engine *e, const FwdParams &p, int frames, bool fuse) {
+int dispatch_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse) {
     if (frames == 0) {
-        int rc = dispatch_pass2_f<false>(e, p, 0);
-        return rc ? rc : dispatch_pass2_f<true>(e, p, 0);
+        int rc = dispatch_pass2_f<0>(e, p, 0);
+        if (!rc) rc = dispatch_pass2_f<1>(e, p, 0);
+        return rc ? rc : dispatch_pass2_f<2>(e, p, 0);
     }
-    return fuse ? dispatch_pass2_f<true>(e, p, frames) : dispatch_pass2_f<false>(e, p, frames);
+    if (fuse == 1) return dispatch_pass2_f<1>(e, p, frames);
+    if (fuse == 2) return dispatch_pass2_f<2>(e, p, frames);
+    return dispatch_pass2_f<0>(e, p, frames);
 }
 
 // forward FFT + pyramid for `frames` consecutive frames starting at ring hop `hop0`
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D uint32 tensor {inner, rows} with row pitch = inner * 4 bytes, box {box_inner, 256}
+int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t rows, uint32_t box_inner) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {inner * 4};
+    cuuint32_t box[2] = {box_inner, 256};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+bool tma_path(const b200_engine *e) {
+    return e->opt_tma && e->tma_ok && e->log2M == 20 && e->in_format == B200_FMT_F32;
+}
+
+int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
+    e->tma_ok = false;
+    if (e->log2M != 20) return 0;
+    if (getenv("B200_NO_TMA")) return 0;
+    CU(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
+    const uint32_t wbox = e->is_real ? 2 * kTmaT : kTmaT;
+    int rc = make_map_2d(&e->window_map, e->d_window, e->is_real ? 2 * kS : kS, kS, wbox);
+    if (rc) return rc;
+    CU(cudaFuncSetAttribute(fft_pass1_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass1C));
+    CU(cudaFuncSetAttribute(fft_pass1_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass1R));
+    CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
+    CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
+    CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
+    e->tma_ok = true;
+    return 0;
+}
+
+int tma_ring_map(b200_engine *e) {  // whenever the hop ring is (re)allocated
+    if (!e->tma_ok) return 0;
+    return make_map_2d(&e->ring_map, e->d_ring, 2 * kS, (uint64_t)e->nhops * (kS / 2), 2 * kTmaT);
+}
+
+int launch_tma_pass1(b200_engine *e, const FwdParams &p, int frames) {
+    const int nsplit = frames >= 2 ? 2 : 1;  // two CTAs share a column tile (even / odd frames): one wave on 2 CTAs per SM
+    const int grid = (kS / kTmaT) * nsplit;
+    if (e->is_real)
+        fft_pass1_tma_kernel<true><<<grid, kTmaThreads, TmaSmem::kPass1R, e->stream>>>(p, e->ring_map, e->window_map, frames,
+                                                                                       nsplit);
+    else
+        fft_pass1_tma_kernel<false><<<grid, kTmaThreads, TmaSmem::kPass1C, e->stream>>>(p, e->ring_map, e->window_map, frames,
+                                                                                        nsplit);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse) {
+    const int total = (kS / kTmaT) * frames;
+    const int grid = std::min(total, 2 * e->num_sms);
+    if (fuse == 1) fft_pass2_tma_kernel<1><<<grid, kTmaThreads, TmaSmem::kPass2, e->stream>>>(p, frames);
+    else if (fuse == 2) fft_pass2_tma_kernel<2><<<grid, kTmaThreads, TmaSmem::kPass2, e->stream>>>(p, frames);
+    else fft_pass2_tma_kernel<0><<<grid, kTmaThreads, TmaSmem::kPass2, e->stream>>>(p, frames);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int bank_acquire(b200_engine *e) {
     // the forward stream may only overwrite a bank once the clients that read it are done
     if (e->banks > 1 && e->cli_pending[e->cur_bank]) {
@@ -278,7 +377,7 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         p.additional = 0;
         p.npeers = 0;
     }
-    const bool fuse = !e->is_real && e->opt_fused_pyramid;
+    const int fuse = e->is_real ? 0 : e->opt_fused_pyramid;  // 0 none, 1 full epilogue in pass 2, 2 |X|^2 from pass 2
     int base_level = 0;
     while ((1 << base_level) < e->sp2.T) base_level++;
     p.quant = e->quant_ptr();
@@ -287,9 +386,14 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     p.levels = e->levels;
     p.size_log2 = e->size_log2;
     int rc = 0;
-    if (e->opt_stage_mask & 1) rc = dispatch_pass1(e, p, frames);
+    const bool tma = tma_path(e);
+    if (tma) {  // pass-2 TMA kernels use T = kTmaT rows per tile
+        base_level = 0;
+        while ((1 << base_level) < kTmaT) base_level++;
+    }
+    if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
     if (rc) return rc;
-    if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames, fuse);
+    if (e->opt_stage_mask & 2) rc = tma ? launch_tma_pass2(e, p, frames, fuse) : dispatch_pass2(e, p, frames, fuse);
     if (rc) return rc;
     if (!(e->opt_stage_mask & 4)) return 0;
 
@@ -309,15 +413,16 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     q.TLr = e->d_TLr;
     q.THr = e->d_THr;
     q.pscratch = e->d_pscratch;
-    q.base_level = fuse ? base_level : 0;
-    q.ntiles = e->sp1.S / e->sp2.T;
+    q.base_level = fuse == 1 ? base_level : 0;
+    q.ntiles = fuse == 2 ? e->sp1.S : (tma ? kS / kTmaT : e->sp1.S / e->sp2.T);
     q.N2 = e->sp2.S;
     q.npeers = e->is_real ? e->npeers : 0;
     for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i];
     if (e->levels > q.base_level) {
         dim3 grid((unsigned)((e->R >> q.base_level) / 1024), frames);
         if (e->is_real) pyramid_kernel<PYR_R2C><<<grid, 256, 0, e->stream>>>(q);
-        else if (fuse) pyramid_kernel<PYR_SCRATCH><<<grid, 256, 0, e->stream>>>(q);
+        else if (fuse == 1) pyramid_kernel<PYR_SCRATCH><<<grid, 256, 0, e->stream>>>(q);
+        else if (fuse == 2) pyramid_kernel<PYR_POWER><<<grid, 256, 0, e->stream>>>(q);
         else pyramid_kernel<PYR_SPEC><<<grid, 256, 0, e->stream>>>(q);
         e->launches++;
         CU(cudaGetLastError());
@@ -383,6 +488,10 @@ int plan_common(b200_engine *e, bool is_real) {
         rc = dispatch_pass2(e, none, 0, false);
         if (rc) return rc;
     }
+    {
+        int rc = tma_prepare(e);
+        if (rc) return rc;
+    }
     e->planned = true;
     return 0;
 }
@@ -407,7 +516,7 @@ int alloc_batch(b200_engine *e, int frames) {
     e->cur_bank = 0;
     for (int b = 0; b < 4; b++) e->cli_pending[b] = false;
     CU(cudaMalloc(&e->d_ptop, sizeof(float) * std::max<size_t>(1, e->R / 1024) * frames));
-    CU(cudaMalloc(&e->d_pscratch, sizeof(float) * (size_t)(e->sp1.S / e->sp2.T) * e->sp2.S * frames));
+    CU(cudaMalloc(&e->d_pscratch, sizeof(float) * e->M * frames));  // |X|^2 of every bin (mode 2) or per-tile sums (mode 1)
     e->batch = frames;
     return 0;
 }
@@ -421,7 +530,7 @@ int alloc_ring(b200_engine *e, size_t nhops) {
     e->head = -1;
     e->last_a2 = nullptr;
     e->frame_hop0 = -1;
-    return 0;
+    return tma_ring_map(e);
 }
 
 int load_common(b200_engine *e, const void *a1, const void *a2) {
@@ -719,7 +828,11 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_RELOAD_BOTH: e->opt_reload_both = value ? 1 : 0; return 0;
     case B200_OPT_HOST_MIRROR: e->opt_mirror = value & 3; return 0;
     case B200_OPT_STAGE_MASK: e->opt_stage_mask = value & 7; return 0;
-    case B200_OPT_FUSED_PYRAMID: e->opt_fused_pyramid = value ? 1 : 0; return 0;
+    case B200_OPT_FUSED_PYRAMID:
+        if (value < 0 || value > 2) return fail(B200_EINVAL, "fused pyramid mode must be 0, 1 or 2");
+        e->opt_fused_pyramid = value;
+        return 0;
+    case B200_OPT_TMA: e->opt_tma = value ? 1 : 0; return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
         if (value != e->in_format) {

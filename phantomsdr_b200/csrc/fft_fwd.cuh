@@ -79,8 +79,9 @@ __device__ __forceinline__ float2 load_sample(const void *hop, int fmt, size_t e
 // ------------------------------------------------------------------------------------------------
 // pass 1: grid (N2/T, frames), block T*max(RA,RB)
 // ------------------------------------------------------------------------------------------------
-template <int RA, int RB, int T, bool RAW>
+template <int RA, int RB, int T, bool RAW, bool REAL>
 __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const FwdParams p) {
+    constexpr int SHIFT = REAL ? 0 : 1;  // the IQ display shift exists only for c2c (fft_impl.cpp:148-150)
     constexpr int PAD = (T < 16) ? (16 - T) : 0;   // keep the two r-rows of a half-warp on disjoint banks
     constexpr int ROW = RA * T + PAD;
     extern __shared__ float2 sm[];
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
             const size_t idx = (size_t)(r + RB * j) * N2 + n2;  // complex element within the frame
             // first half of the frame (j < RA/2) comes from the older hop
             float2 x = (j < RA / 2) ? load_sample(hopA, fmt, idx) : load_sample(hopB, fmt, idx - half);
-            if (p.is_real) {
+            if constexpr (REAL) {
                 float2 w = __ldg(reinterpret_cast<const float2 *>(p.window) + idx);
                 x.x *= w.x;
                 x.y *= w.y;
@@ -136,10 +137,10 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
 #pragma unroll
         for (int s = 0; s < RB; s++) {
             const int k1 = q + RA * s;
-            int u1 = k1 - p.shift;
+            int u1 = k1 - SHIFT;
             if (u1 < 0) u1 += N1;
             // exponent of W_M: n2*k1, or the one-slot rotation N1*n2 for the IQ k1 = 0 row
-            const unsigned e = (p.shift && k1 == 0) ? (unsigned)N1 * (unsigned)n2 : (unsigned)n2 * (unsigned)k1;
+            const unsigned e = (SHIFT && k1 == 0) ? (unsigned)N1 * (unsigned)n2 : (unsigned)n2 * (unsigned)k1;
             const float2 tw = cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + (e >> 10)));
             Y[(size_t)u1 * N2 + n2] = cmul(u[s], tw);
         }
@@ -189,7 +190,9 @@ template <int NB> __device__ __forceinline__ void store_packed(int8_t *dst, cons
 template <int T> struct Log2 { static constexpr int v = 1 + Log2<T / 2>::v; };
 template <> struct Log2<1> { static constexpr int v = 0; };
 
-template <int RA, int RB, int T, bool FUSE>
+// FUSE: 0 = spectrum only; 1 = whole waterfall epilogue (levels 0..log2(T)-1 quantised here); 2 = |X|^2 stored
+// straight from the FFT registers into the power scratch [u2][u1], quantiser + pyramid in pyramid_kernel<PYR_POWER>
+template <int RA, int RB, int T, int FUSE>
 __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const FwdParams p) {
     constexpr int TPC = CMax<RA, RB>::v;
     constexpr int ROW = RA * T + 1;  // odd stride: lanes along r hit distinct banks
@@ -238,16 +241,26 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
                 const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
                 out[k] = val;
                 if (k < (size_t)p.additional) out[M + k] = val;  // IQ wrap tail, src/fft.cpp:96-97
+                if constexpr (FUSE == 1) pw[s] = __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
+                if constexpr (FUSE == 2)
+                    p.pscratch[(size_t)frame * M + (size_t)u2 * N1 + u1] =
+                        __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
+            }
+            if (p.npeers > 0) {  // NVLink peer copies of the frame (multi-GPU ingest rank only), off the common path
                 for (int pe = 0; pe < p.npeers; pe++) {
                     float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
-                    po[k] = val;
-                    if (k < (size_t)p.additional) po[M + k] = val;
+#pragma unroll
+                    for (int s = 0; s < RB; s++) {
+                        const size_t k = ((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1);
+                        const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
+                        po[k] = val;
+                        if (k < (size_t)p.additional) po[M + k] = val;
+                    }
                 }
-                if constexpr (FUSE) pw[s] = __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
             }
         }
     }
-    if constexpr (FUSE) {
+    if constexpr (FUSE == 1) {
         // Waterfall epilogue (src/fft_impl.cpp:24-61,146-173): |X|^2 of this CTA's T x N2 bins goes through
         // shared memory so that one thread owns one display run of T bins and writes whole words.
         float *pt = reinterpret_cast<float *>(sm);
@@ -301,7 +314,7 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
     }
 }
 
-enum { PYR_SPEC = 0, PYR_R2C = 1, PYR_SCRATCH = 2 };
+enum { PYR_SPEC = 0, PYR_R2C = 1, PYR_SCRATCH = 2, PYR_POWER = 3 };
 
 struct PyrParams {
     float2 *spec;            // spectrum (PYR_SPEC: input, already normalised; PYR_R2C: OUTPUT written here)
@@ -373,6 +386,16 @@ template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const 
             for (int pe = 0; pe < p.npeers; pe++) (p.peers[pe] + (size_t)frame * p.spec_stride)[k] = x;
             pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
         }
+    } else if constexpr (MODE == PYR_POWER) {
+        // |X|^2 left by FFT pass 2 in [u2][u1] order: display bin d = u1 + N1 * ((u2 + N2/2) mod N2)
+        const int N1 = p.ntiles, N2 = p.N2;  // (ntiles carries N1 in this mode)
+        const size_t u1 = d0 & (size_t)(N1 - 1), d2 = d0 / N1;
+        const size_t u2 = (d2 + (N2 >> 1)) & (size_t)(N2 - 1);
+        const float4 f = *reinterpret_cast<const float4 *>(p.pscratch + (size_t)frame * R + u2 * N1 + u1);
+        pw[0] = f.x;
+        pw[1] = f.y;
+        pw[2] = f.z;
+        pw[3] = f.w;
     } else {
         const float *scr = p.pscratch + (size_t)frame * p.ntiles * p.N2;
 #pragma unroll

@@ -1,0 +1,323 @@
+// TMA-fed variants of the two FFT passes for the 2^20-point complex transform (the headline configs:
+// 2^20 c2c and 2^21 r2c). Same mathematics and data layout as fft_fwd.cuh; what changes is how the data
+// reaches the butterflies and where the twiddles live:
+//   * two CTAs of eight warps per SM; thread 0 of a CTA streams the CTA's NEXT tile into shared memory with TMA (pass 1: cp.async.bulk.tensor 2-D boxes of the strided column tile;
+//     pass 2: cp.async.bulk 1-D copies of contiguous rows) as soon as the stage buffer is free again, i.e.
+//     while the consumers are still in the second register DFT, the twiddle multiply and the global stores
+//     of the current tile; a "full" mbarrier (expect_tx / complete_tx) tells the consumers when it has landed;
+//   * the stage buffer doubles as the shared-memory exchange buffer between the two register DFTs; the |X|^2
+//     tile of the fused waterfall epilogue has its own 36 KiB so the stage is released before the epilogue;
+//   * pass 1 keeps ONE column tile per CTA across the frames of a batch: its slice of the Hann window is
+//     fetched once, the intra-pass twiddles sit in shared memory, and the inter-pass twiddles
+//     W_M^(n2*(q+32s)) = G_a * B^b (s = 4a+b) are held as 8+3 register values per thread.
+#pragma once
+#include <cuda.h>
+#include <cstdint>
+#include "fft_fwd.cuh"
+
+namespace b200 {
+
+constexpr int kTmaT = 8;            // columns (rows) per tile
+constexpr int kTmaThreads = 256;    // 8 warps: T * 32 threads; thread 0 also drives TMA
+constexpr int kS = 1024;            // sub-transform length of both passes
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { __syncthreads(); }
+
+struct TmaSmem {
+    static constexpr int kRow1 = 32 * kTmaT + 8;                        // pass-1 exchange row pitch (float2)
+    static constexpr int kRow2 = 32 * kTmaT + 1;                        // pass-2 exchange row pitch (float2)
+    static constexpr size_t kStage = sizeof(float2) * 32 * kRow1;       // >= 64 KiB tile, >= either exchange layout
+    static constexpr size_t kTwA = sizeof(float2) * 32 * 32;            // intra-pass twiddles W_1024^(r q)
+    static constexpr size_t kWindowC = sizeof(float) * kS * kTmaT;      // 32 KiB Hann slice, c2c (one weight per IQ pair)
+    static constexpr size_t kWindowR = 2 * kWindowC;                    // 64 KiB, r2c (one weight per real sample)
+    static constexpr int kPP = kTmaT + 1;                               // power tile pitch (floats): odd, conflict-free
+    static constexpr size_t kPower = sizeof(float) * kS * kPP;          // 36 KiB |X|^2 tile of the fused waterfall epilogue
+    static constexpr size_t kBars = 64;
+    static constexpr size_t kPass1C = kStage + kTwA + kWindowC + kBars;
+    static constexpr size_t kPass1R = kStage + kTwA + kWindowR + kBars;
+    static constexpr size_t kPass2 = kStage + kTwA + kPower + kBars;
+};
+static_assert(TmaSmem::kStage >= sizeof(float2) * kS * kTmaT, "stage must hold a tile");
+static_assert(TmaSmem::kStage >= sizeof(float2) * 32 * TmaSmem::kRow2, "stage must hold the pass-2 exchange");
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: grid = (N2/T) * nsplit CTAs. CTA (tile, part) handles the frames f == part (mod nsplit) of column tile
+// `tile`; block = 256 consumers + 1 producer warp.
+//   ring_map  : hop ring as a 2-D uint32 tensor {2*N2, nhops*N1/2}, box {2*T, 256}
+//   window_map: Hann window as {N2 (c2c) | 2*N2 (r2c), N1}, box {T | 2*T, 256}
+// ------------------------------------------------------------------------------------------------
+template <bool REAL>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+    fft_pass1_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap ring_map,
+                         const __grid_constant__ CUtensorMap window_map, int nframes, int nsplit) {
+    constexpr int T = kTmaT, RA = 32, RB = 32, N1 = kS, N2 = kS;
+    constexpr int SHIFT = REAL ? 0 : 1;
+    constexpr int ROW = TmaSmem::kRow1;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    float2 *twA = reinterpret_cast<float2 *>(smem_raw + TmaSmem::kStage);
+    float *win = reinterpret_cast<float *>(smem_raw + TmaSmem::kStage + TmaSmem::kTwA);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + TmaSmem::kStage + TmaSmem::kTwA +
+                                                  (REAL ? TmaSmem::kWindowR : TmaSmem::kWindowC));
+    uint64_t *full = bars, *wbar = bars + 1;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x / nsplit;
+    const int part = blockIdx.x - tile * nsplit;
+    if (tid == 0) {
+        mbar_init(full, 1);
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    for (int i = tid; i < 32 * 32; i += kTmaThreads) twA[i] = p.twA1[i];
+    __syncthreads();
+
+    // thread 0 drives TMA: the window slice once, then one tile ahead of the consumers
+    auto issue_tile = [&](int f) {
+        mbar_expect_tx(full, sizeof(float2) * N1 * T);
+        const int hopA = (p.hop0 + f) % p.nhops, hopB = (p.hop0 + f + 1) % p.nhops;
+        // rows 0..511 of the frame come from the older hop, 512..1023 from the newer one
+        tma_load_2d(smem_raw + 0 * 16384, &ring_map, tile * T * 2, hopA * (N1 / 2), full);
+        tma_load_2d(smem_raw + 1 * 16384, &ring_map, tile * T * 2, hopA * (N1 / 2) + 256, full);
+        tma_load_2d(smem_raw + 2 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2), full);
+        tma_load_2d(smem_raw + 3 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2) + 256, full);
+    };
+    if (tid == 0) {
+        constexpr uint32_t kWinBytes = sizeof(float) * N1 * T * (REAL ? 2 : 1);
+        mbar_expect_tx(wbar, kWinBytes);
+        for (int b = 0; b < 4; b++)
+            tma_load_2d(reinterpret_cast<unsigned char *>(win) + b * (kWinBytes / 4), &window_map, tile * T * (REAL ? 2 : 1),
+                        b * 256, wbar);
+        if (part < nframes) issue_tile(part);
+    }
+
+    // ===== consumers =====
+    const int c = tid % T;
+    const int r = tid / T;
+    const int q = r;
+    const int n2 = tile * T + c;
+    const size_t M = (size_t)N1 * N2;
+    // inter-pass twiddles of this thread, W_M^(n2*k1) for k1 = q + 32 s with s = 4a + b:
+    //   G[a] = W_M^(n2*(q + 128 a)),  B[b-1] = W_M^(32*n2*b)   ->   tw(s) = G[a] * B[b-1]  (b = 0: G[a])
+    // (the IQ k1 = 0 row, q = 0 and s = 0, carries the one-slot rotation W_M^(N1*n2) instead)
+    float2 G[8], B[3];
+    {
+        auto tw_lookup = [&](unsigned e) { return cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + ((e >> 10) & 1023u))); };
+#pragma unroll
+        for (int a = 0; a < 8; a++) G[a] = tw_lookup((unsigned)n2 * (unsigned)(q + 128 * a));
+#pragma unroll
+        for (int b = 1; b < 4; b++) B[b - 1] = tw_lookup((unsigned)n2 * 32u * (unsigned)b);
+    }
+    const float2 rot0 = cmul(__ldg(p.TL + (((unsigned)N1 * (unsigned)n2) & 1023u)), __ldg(p.TH + (((unsigned)N1 * (unsigned)n2) >> 10)));
+    mbar_wait(wbar, 0);
+    int it = 0;
+    for (int f = part; f < nframes; f += nsplit, it++) {
+        mbar_wait(full, it & 1);
+        float2 v[RA];
+#pragma unroll
+        for (int j = 0; j < RA; j++) {
+            float2 x = sm[(r + RB * j) * T + c];
+            if constexpr (REAL) {
+                const float2 w = reinterpret_cast<const float2 *>(win)[(r + RB * j) * T + c];
+                x.x *= w.x;
+                x.y *= w.y;
+            } else {
+                const float w = win[(r + RB * j) * T + c];
+                x.x *= w;
+                x.y *= w;
+            }
+            v[j] = x;
+        }
+        consumer_sync();  // the raw tile is in registers: the stage becomes the exchange buffer
+        RegDft<RA>::run(v);
+        sm[r * ROW + c] = v[0];
+#pragma unroll
+        for (int qq = 1; qq < RA; qq++) sm[r * ROW + qq * T + c] = cmul(v[qq], twA[qq * RB + r]);
+        consumer_sync();
+        float2 u[RB];
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) u[rr] = sm[rr * ROW + q * T + c];
+        consumer_sync();  // exchange consumed: the next tile streams in while this one is finished
+        if (tid == 0 && f + nsplit < nframes) {
+            fence_proxy_async();  // generic-proxy accesses to the stage are ordered before the TMA write
+            issue_tile(f + nsplit);
+        }
+        RegDft<RB>::run(u);
+        float2 *Y = p.Y + (size_t)f * M + n2;
+#pragma unroll
+        for (int s = 0; s < RB; s++) {
+            const int k1 = q + RA * s;
+            int u1 = k1 - SHIFT;
+            if (u1 < 0) u1 += N1;
+            float2 tw = (s & 3) ? cmul(G[s >> 2], B[(s & 3) - 1]) : G[s >> 2];
+            if (SHIFT && s == 0 && q == 0) tw = rot0;  // the IQ k1 = 0 row: one-slot rotation
+            Y[(size_t)u1 * N2] = cmul(u[s], tw);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: persistent grid (2 CTAs per SM); tile i = (frame, row tile) goes to CTA i % gridDim.x.
+// ------------------------------------------------------------------------------------------------
+template <int FUSE>
+__global__ void __launch_bounds__(kTmaThreads, 2) fft_pass2_tma_kernel(const FwdParams p, int nframes) {
+    constexpr int T = kTmaT, RA = 32, RB = 32, N1 = kS, N2 = kS;
+    constexpr int ROW = TmaSmem::kRow2;
+    constexpr int PP = TmaSmem::kPP;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float2 *sm = reinterpret_cast<float2 *>(smem_raw);
+    float2 *twA = reinterpret_cast<float2 *>(smem_raw + TmaSmem::kStage);
+    float *pt = reinterpret_cast<float *>(smem_raw + TmaSmem::kStage + TmaSmem::kTwA);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + TmaSmem::kStage + TmaSmem::kTwA + TmaSmem::kPower);
+
+    const int tid = threadIdx.x;
+    const int tiles_per_frame = N1 / T;
+    const int total = tiles_per_frame * nframes;
+    const size_t M = (size_t)N1 * N2;
+    if (tid == 0) {
+        mbar_init(full, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    for (int i = tid; i < 32 * 32; i += kTmaThreads) twA[i] = p.twA2[i];
+    __syncthreads();
+    auto issue_tile = [&](int i) {  // T consecutive rows of Y are one contiguous 64 KiB block
+        const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
+        mbar_expect_tx(full, sizeof(float2) * N2 * T);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(p.Y + (size_t)frame * M + (size_t)tile * T * N2);
+        for (int k = 0; k < 4; k++) bulk_load_1d(smem_raw + k * 16384, src + k * 16384, 16384, full);
+    };
+    if (tid == 0 && (int)blockIdx.x < total) issue_tile(blockIdx.x);
+
+    int it = 0;
+    for (int i = blockIdx.x; i < total; i += gridDim.x, it++) {
+        const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
+        mbar_wait(full, it & 1);
+        {   // stage A: lanes along n2
+            const int r = tid % 32;
+            const int c = tid / 32;
+            float2 v[RA];
+#pragma unroll
+            for (int j = 0; j < RA; j++) v[j] = sm[c * N2 + r + RB * j];
+            consumer_sync();
+            RegDft<RA>::run(v);
+            sm[r * ROW + c] = v[0];
+#pragma unroll
+            for (int qq = 1; qq < RA; qq++) sm[r * ROW + qq * T + c] = cmul(v[qq], twA[qq * RB + r]);
+        }
+        consumer_sync();
+        const int c = tid % T;
+        const int q = tid / T;
+        float2 u[RB];
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) u[rr] = sm[rr * ROW + q * T + c];
+        consumer_sync();  // exchange consumed: the next tile streams in while this one is finished
+        if (tid == 0 && i + (int)gridDim.x < total) {
+            fence_proxy_async();
+            issue_tile(i + gridDim.x);
+        }
+        RegDft<RB>::run(u);
+        float2 *out = p.out + (size_t)frame * p.out_stride;
+        const unsigned u1 = tile * T + c;
+        const float scale = p.scale;
+        float pw[RB];
+#pragma unroll
+        for (int s = 0; s < RB; s++) {
+            const unsigned u2 = q + RA * s;
+            const size_t k = ((size_t)u1 + (size_t)N1 * u2 + p.shift) & (M - 1);
+            const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
+            out[k] = val;
+            if (k < (size_t)p.additional) out[M + k] = val;  // IQ wrap tail, src/fft.cpp:96-97
+            if constexpr (FUSE == 1) pw[s] = __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
+            if constexpr (FUSE == 2)
+                p.pscratch[(size_t)frame * M + (size_t)u2 * N1 + u1] = __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
+        }
+        if (p.npeers > 0) {  // NVLink peer copies of the frame (multi-GPU ingest rank only), off the common path
+            for (int pe = 0; pe < p.npeers; pe++) {
+                float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
+#pragma unroll
+                for (int s = 0; s < RB; s++) {
+                    const size_t k = ((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1);
+                    const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
+                    po[k] = val;
+                    if (k < (size_t)p.additional) po[M + k] = val;
+                }
+            }
+        }
+        if constexpr (FUSE == 1) {
+            // (the previous tile's epilogue readers are past the two barriers above)
+#pragma unroll
+            for (int s = 0; s < RB; s++) pt[(q + RA * s) * PP + c] = pw[s];
+            consumer_sync();
+            constexpr int LT = Log2<T>::v;
+            const int L = p.levels;
+            int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
+            float *scr = p.pscratch + ((size_t)frame * (N1 / T) + tile) * N2;
+#pragma unroll
+            for (int u2 = tid; u2 < N2; u2 += kTmaThreads) {
+                const unsigned d2 = (u2 + (N2 >> 1)) & (N2 - 1);
+                const size_t dbase = (size_t)tile * T + (size_t)N1 * d2;
+                float vv[T];
+#pragma unroll
+                for (int k = 0; k < T; k++) vv[k] = pt[u2 * PP + k];
+                size_t lvl_off = 0;
+                static_for<LT>([&](auto lvc) {
+                    constexpr int lv = decltype(lvc)::value;
+                    constexpr int CNT = T >> lv;
+                    if (lv < L) {
+                        unsigned w[(CNT + 3) / 4];
+#pragma unroll
+                        for (int k = 0; k < (CNT + 3) / 4; k++) w[k] = 0;
+#pragma unroll
+                        for (int k = 0; k < CNT; k++)
+                            w[k / 4] |= (unsigned)quantize_dev(vv[k], p.size_log2 - lv) << (8 * (k % 4));
+                        store_packed<CNT>(quant + lvl_off + (dbase >> lv), w);
+                    }
+                    lvl_off += M >> lv;
+#pragma unroll
+                    for (int k = 0; k < CNT / 2; k++) vv[k] = __fadd_rn(vv[2 * k], vv[2 * k + 1]);
+                });
+                scr[d2] = vv[0];
+            }
+        }
+    }
+}
+
+}  // namespace b200
