@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--real", action="store_true", help="r2c input (cfg 3 shape)")
     ap.add_argument("--clients", type=int, default=1024, help="demod clients per GPU")
     ap.add_argument("--ring", type=int, default=64, help="hops resident in HBM = frames per step")
-    ap.add_argument("--batch", type=int, default=8, help="frames per kernel launch")
+    ap.add_argument("--batch", type=int, default=16, help="frames per kernel launch")
     ap.add_argument("--banks", type=int, default=2, help="pipeline depth: clients of batch k overlap the FFT of batch k+1")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
