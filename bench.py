@@ -418,9 +418,16 @@ def run_b200(args):
         torch.cuda.synchronize()
         breakdown["clients_us_per_frame"] = round(a.elapsed_time(b) * 1e3 / (reps * F), 3)
         breakdown["forward_us_per_frame"] = round(t_fwd * 1e6, 3)
+        traffic = None
+        try:
+            tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+            if tr.get("batch") == F and not cfg.is_real and args.fft_log2 == 20:
+                traffic = tr["dram_bytes_per_launch_group"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "forward FFT + waterfall (fft_pass1 + fft_pass2 + pyramid, one launch each per "
                                              f"{F} frames)",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "peak_source": which, "algorithmic_bytes_per_frame": bytes_frame,
                     "algorithmic_bytes_per_launch_group": bytes_frame * F, "us_per_frame": t_fwd * 1e6}
 
