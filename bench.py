@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-frames", type=int, default=64)
+    ap.add_argument("--e2e-frames", type=int, default=256)
     ap.add_argument("--mgpu-mode", default="spectrum", choices=["spectrum"],
                     help="what crosses NVLink per frame (north_star: the spectrum frame)")
     return ap.parse_args()
@@ -431,54 +431,56 @@ def run_b200(args):
                     "peak_source": which, "algorithmic_bytes_per_frame": bytes_frame,
                     "algorithmic_bytes_per_launch_group": bytes_frame * F, "us_per_frame": t_fwd * 1e6}
 
-    # ---- e2e: same frames through the reference-facing C-ABI with host buffers ----
+    # ---- e2e: same frames through the reference-facing C-ABI with HOST buffers ----
+    # b200_submit_block / b200_wait_block = load_*_input + execute + signal_loop for F frames per call, pipelined:
+    # H2D of block k+1, kernels of block k, D2H of block k's results (pyramid + PCM/pwr/valid) on three streams.
     e2e = None
     if not args.no_e2e:
-        e2e_frames = args.e2e_frames
-        nbuf = 4
-        host = [eng.malloc(cfg.hop_floats) for _ in range(nbuf)]
-        rs = np.random.default_rng(0x5EED + 3 + rank)
-        for hb in host:
-            hb[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
         eng.join_streams()
         eng.sync()
-        eng.select_bank(0)
-        eng.set_option(OPT_HOST_MIRROR, 2)  # clients live on the GPU: only the pyramid returns to the host
-        outs = eng.clients_fetch(0)
-        load = eng.load_real_input if cfg.is_real else eng.load_complex_input
-        L = eng.L
+        h = n // 2
+        nblk = max(2, args.e2e_frames // F)
+        rs = np.random.default_rng(0x5EED + 3 + rank)
+        sets = []
+        for _ in range(2):  # two blocks in flight -> two sets of pinned host buffers
+            halves = [eng.malloc(cfg.hop_floats) for _ in range(F)]
+            for hb in halves:
+                hb[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
+            sets.append(dict(halves=halves,
+                             pcm=eng.pinned(4 * F * args.clients * h, np.int32),
+                             pwr=eng.pinned(4 * F * args.clients, np.float32),
+                             valid=eng.pinned(F * args.clients, np.uint8),
+                             pyr=eng.pinned(F * eng.pyramid_bytes, np.int8)))
+        prime = eng.malloc(cfg.hop_floats)
+        prime[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
 
-        def e2e_pass(nf, f0):
-            for f in range(nf):
-                load(host[(f0 + f) % nbuf], host[(f0 + f + 1) % nbuf])
-                eng.execute()
-                _ffi_check(L.b200_clients_execute(eng.h, f0 + f, outs[0].ctypes.data, outs[1].ctypes.data,
-                                                  outs[2].ctypes.data))
+        def e2e_run(blocks, f0):
+            eng.stream_prime(prime)
+            for k in range(blocks):
+                st = sets[k & 1]
+                if k >= 2:
+                    eng.wait_block()  # block k-2 used this buffer set
+                eng.submit_block(st["halves"], f0 + k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
+            for _ in range(min(2, blocks)):
+                eng.wait_block()
 
-        from phantomsdr_b200._ffi import check as _ffi_check
-
-        if world > 1:
-            # every rank drives its own full host->device path in the e2e leg (independent streams)
-            pass
-        e2e_pass(8, 0)
+        e2e_run(3, 0)  # warm-up
         barrier()
         t0 = time.perf_counter()
-        e2e_pass(e2e_frames, 8)
-        torch.cuda.synchronize()
+        e2e_run(nblk, 3 * F)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         hbytes = cfg.hop_floats * 4
-        dbytes = eng.pyramid_bytes + args.clients * (n // 2) * 4 + args.clients * 5
-        e2e = {"value": world * e2e_frames * cfg.hop_samples / dt / 1e6, "unit": UNIT,
+        dbytes = eng.pyramid_bytes + args.clients * h * 4 + args.clients * 5
+        e2e = {"value": world * nblk * F * cfg.hop_samples / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": hbytes * H, "d2h_bytes_per_step": dbytes * H,
-               "frames_timed": e2e_frames,
-               "path": "b200_load_complex_input(pinned host halves) -> b200_execute (pyramid mirrored to host) -> "
-                       "b200_clients_execute (PCM/pwr/valid to host), one synchronous call chain per frame"}
-        for hb in host:
-            eng.free(hb)
+               "frames_timed": nblk * F,
+               "path": f"b200_submit_block / b200_wait_block: {F} frames per call from pinned host halves "
+                       "(H2D of every new half) -> forward FFT + pyramid -> clients -> D2H of the int8 pyramid and "
+                       "PCM/pwr/valid of every frame; two blocks in flight; every rank drives its own host path"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -222,6 +222,23 @@ int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_o
 int b200_clients_read_pre_dc(b200_engine *e, float *out);
 
 /* ------------------------------------------------------------------------------------------
+ * Pipelined block form of the same host-buffer path: load -> execute -> signal_loop for `nframes` frames per
+ * call, with the host->device copy of block k+1, the kernels of block k and the device->host copy of block
+ * k's results running on three streams (up to two blocks in flight). Needs b200_set_batch_frames(F),
+ * b200_set_pipeline(>= 2) and a hop ring of >= 2F+2 halves.
+ *   b200_stream_prime(older_half)     : the half that precedes the first frame (the reference reads two halves
+ *                                       before its first transform, src/fft.cpp:50-67)
+ *   b200_submit_block(new_halves[nframes], ...): frame f of the block = (previous newest half | new_halves[f]);
+ *       outputs (page-locked host memory; any may be NULL): pcm [nframes][max_clients][n/2], pwr / valid
+ *       [nframes][max_clients], pyramid [nframes][b200_pyramid_bytes()]. Returns at once.
+ *   b200_wait_block()                 : blocks until the OLDEST submitted block's outputs are complete.
+ * ------------------------------------------------------------------------------------------ */
+int b200_stream_prime(b200_engine *e, const void *older_half);
+int b200_submit_block(b200_engine *e, const void *const *new_halves, int nframes, uint64_t frame_num0, int32_t *pcm_out,
+                      float *pwr_out, uint8_t *valid_out, int8_t *pyramid_out);
+int b200_wait_block(b200_engine *e);
+
+/* ------------------------------------------------------------------------------------------
  * Waterfall slot group - replaces N x WaterfallClient::send_waterfall (src/waterfall.cpp:44-51)
  * and the level-offset math of waterfall_loop (src/websocket.cpp:207-236).
  * ------------------------------------------------------------------------------------------ */

@@ -67,6 +67,9 @@ SIGNATURES = {
     "b200_device_valid": (_vp, [_vp]),
     "b200_clients_fetch": (_i, [_vp, _i, _vp, _vp, _vp]),
     "b200_clients_read_pre_dc": (_i, [_vp, _vp]),
+    "b200_stream_prime": (_i, [_vp, _vp]),
+    "b200_submit_block": (_i, [_vp, _pp, _i, _u64, _vp, _vp, _vp, _vp]),
+    "b200_wait_block": (_i, [_vp]),
     "b200_waterfall_gather": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200_launch_count": (_u64, [_vp]),
     "b200_debug_tail_profile": (_i, [_vp, _i, _vp]),

@@ -268,6 +268,24 @@ class B200FFT:
         check(self.L.b200_clients_read_pre_dc(self.h, _ptr(out)))
         return out
 
+    # ---- pipelined host-block streaming -----------------------------------------------------
+    def stream_prime(self, older_half: np.ndarray) -> None:
+        check(self.L.b200_stream_prime(self.h, _ptr(older_half)))
+
+    def submit_block(self, new_halves, frame_num0: int, pcm=None, pwr=None, valid=None, pyramid=None) -> None:
+        """new_halves: sequence of host arrays (one per frame). Outputs: pinned host arrays or None."""
+        n = len(new_halves)
+        arr = (C.c_void_p * n)(*[_ptr(a) for a in new_halves])
+        check(self.L.b200_submit_block(self.h, arr, n, frame_num0, _ptr(pcm), _ptr(pwr), _ptr(valid), _ptr(pyramid)))
+
+    def wait_block(self) -> None:
+        check(self.L.b200_wait_block(self.h))
+
+    def pinned(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """Page-locked host array (through FFT::malloc) viewed as dtype."""
+        a = self.malloc((nbytes + 3) // 4)
+        return a.view(np.uint8)[:nbytes].view(dtype)
+
     # ---- waterfall slot ----------------------------------------------------------------------
     def waterfall_gather(self, levels: Sequence[int], ls: Sequence[int], rs: Sequence[int]):
         """N x send_waterfall (src/waterfall.cpp:44-51): returns one int8 array per client."""

@@ -154,6 +154,13 @@ struct b200_engine {
     int last_client_frames = 0;
     long long *d_prof = nullptr;
 
+    // pipelined host-block streaming (b200_stream_prime / b200_submit_block / b200_wait_block)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_out[2] = {}, ev_ring_free[2] = {};
+    bool blk_pending[2] = {};
+    uint64_t blk_submitted = 0, blk_waited = 0;
+    long stream_head = -1;  // ring index of the newest resident half
+
     uint64_t launches = 0;
 
     size_t format_bytes() const {
@@ -747,6 +754,15 @@ void b200_engine_destroy(b200_engine *e) {
         }
         cudaStreamDestroy(e->cstream);
     }
+    if (e->copy_stream) {
+        cudaStreamSynchronize(e->copy_stream);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(e->ev_in[i]);
+            cudaEventDestroy(e->ev_out[i]);
+            cudaEventDestroy(e->ev_ring_free[i]);
+        }
+        cudaStreamDestroy(e->copy_stream);
+    }
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -1230,6 +1246,100 @@ int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const 
     if (err != cudaSuccess) return fail(B200_ECUDA, "waterfall gather failed: %s", cudaGetErrorString(err));
     // only the clients' own byte ranges of `out` are touched
     for (int i = 0; i < nclients; i++) memcpy(out + dst[i], staged.data() + dst[i], (size_t)len[i]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined host-block streaming: the same load -> execute -> clients path, nframes frames per call, with
+// the H2D of block k+1, the kernels of block k and the D2H of block k's results on three streams.
+// ------------------------------------------------------------------------------------------------
+static int stream_setup(b200_engine *e) {
+    if (e->copy_stream) return 0;
+    CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_ring_free[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int b200_stream_prime(b200_engine *e, const void *older_half) {
+    if (!e || !older_half) return fail(B200_EINVAL, "null argument");
+    if (!e->planned) return fail(B200_ESTATE, "stream_prime before plan");
+    CU(cudaSetDevice(e->device));
+    int rc = stream_setup(e);
+    if (rc) return rc;
+    if (e->banks < 2) return fail(B200_ESTATE, "block streaming needs b200_set_pipeline(>= 2)");
+    if ((long)e->nhops < 2 * (long)e->batch + 2) return fail(B200_ESTATE, "hop ring must hold at least 2*batch+2 halves");
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->cstream) CU(cudaStreamSynchronize(e->cstream));
+    CU(cudaStreamSynchronize(e->copy_stream));
+    const size_t hb = e->hop_samples * e->format_bytes();
+    CU(cudaMemcpyAsync(e->d_ring, older_half, hb, cudaMemcpyHostToDevice, e->copy_stream));
+    CU(cudaStreamSynchronize(e->copy_stream));
+    e->stream_head = 0;
+    e->blk_submitted = e->blk_waited = 0;
+    e->blk_pending[0] = e->blk_pending[1] = false;
+    return 0;
+}
+
+int b200_submit_block(b200_engine *e, const void *const *new_halves, int nframes, uint64_t frame_num0, int32_t *pcm_out,
+                      float *pwr_out, uint8_t *valid_out, int8_t *pyramid_out) {
+    if (!e || !new_halves) return fail(B200_EINVAL, "null argument");
+    if (e->stream_head < 0) return fail(B200_ESTATE, "submit_block before stream_prime");
+    if (nframes < 1 || nframes > e->batch) return fail(B200_EINVAL, "nframes %d outside 1..%d", nframes, e->batch);
+    if (e->blk_submitted - e->blk_waited >= 2) return fail(B200_ESTATE, "two blocks already in flight: call b200_wait_block");
+    CU(cudaSetDevice(e->device));
+    const int slot = (int)(e->blk_submitted & 1);
+    const size_t hb = e->hop_samples * e->format_bytes();
+    char *ring = reinterpret_cast<char *>(e->d_ring);
+    // the ring slots this block overwrites were last read by the forward pass of the block two submissions ago
+    if (e->blk_submitted >= 2) CU(cudaStreamWaitEvent(e->copy_stream, e->ev_ring_free[slot], 0));
+    const long hop0 = e->stream_head;
+    for (int f = 0; f < nframes; f++) {
+        const long dst = (hop0 + 1 + f) % (long)e->nhops;
+        CU(cudaMemcpyAsync(ring + (size_t)dst * hb, new_halves[f], hb, cudaMemcpyHostToDevice, e->copy_stream));
+    }
+    CU(cudaEventRecord(e->ev_in[slot], e->copy_stream));
+    e->stream_head = (hop0 + nframes) % (long)e->nhops;
+    // forward on the engine stream
+    e->cur_bank = slot % e->banks;
+    CU(cudaStreamWaitEvent(e->stream, e->ev_in[slot], 0));
+    int rc = run_forward(e, hop0, nframes);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev_ring_free[slot], e->stream));
+    if (pyramid_out) {
+        // rows of the batch are pyr_stride apart on the device, pyr_bytes apart for the caller
+        CU(cudaMemcpy2DAsync(pyramid_out, e->pyr_bytes, e->quant_ptr(), e->pyr_stride, e->pyr_bytes, nframes,
+                             cudaMemcpyDeviceToHost, e->stream));
+    }
+    cudaStream_t cs = e->client_stream();
+    if (e->have_clients) {
+        rc = run_clients(e, frame_num0, nframes);
+        if (rc) return rc;
+        const size_t mc = e->ca.max_clients, h = e->ca.h;
+        if (pcm_out) CU(cudaMemcpyAsync(pcm_out, e->ca.pcm, sizeof(int32_t) * mc * h * nframes, cudaMemcpyDeviceToHost, cs));
+        if (pwr_out) CU(cudaMemcpyAsync(pwr_out, e->ca.pwr, sizeof(float) * mc * nframes, cudaMemcpyDeviceToHost, cs));
+        if (valid_out) CU(cudaMemcpyAsync(valid_out, e->ca.valid, mc * nframes, cudaMemcpyDeviceToHost, cs));
+    }
+    // block completion = client results on the host and (engine stream) the pyramid on the host
+    CU(cudaEventRecord(e->ev_out[slot], e->stream));
+    CU(cudaStreamWaitEvent(cs, e->ev_out[slot], 0));
+    CU(cudaEventRecord(e->ev_out[slot], cs));
+    e->blk_pending[slot] = true;
+    e->blk_submitted++;
+    return 0;
+}
+
+int b200_wait_block(b200_engine *e) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (e->blk_waited >= e->blk_submitted) return fail(B200_ESTATE, "no block in flight");
+    CU(cudaSetDevice(e->device));
+    const int slot = (int)(e->blk_waited & 1);
+    CU(cudaEventSynchronize(e->ev_out[slot]));
+    e->blk_pending[slot] = false;
+    e->blk_waited++;
     return 0;
 }
 

@@ -1,0 +1,80 @@
+"""GPU: the pipelined host-block API (b200_stream_prime / b200_submit_block / b200_wait_block) must give exactly
+what the per-frame reference-shaped calls give (load_complex_input -> execute -> clients_execute) on the same input."""
+import numpy as np
+import pytest
+
+from phantomsdr_b200 import SpectrumConfig, USB, LSB, AM, FM
+from phantomsdr_b200.synth import SignalSource, make_clients
+from helpers import make_engine, hop_as_floats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("is_real", [False, True])
+def test_block_streaming_equals_per_frame_calls(gpu_required, is_real):
+    cfg = SpectrumConfig(sps=4_370_000 * (2 if is_real else 1), fft_size=(1 << 18) if is_real else (1 << 17), is_real=is_real)
+    n, h = cfg.audio_fft_size, cfg.audio_fft_size // 2
+    F, nblocks, nc = 4, 3, 12
+    src = SignalSource(cfg, seed=21)
+    hops = [hop_as_floats(src.next_hop()).copy() for _ in range(F * nblocks + 1)]
+    specs = make_clients(cfg, nc, modes=(USB, LSB, AM, FM), tones=[src.display_bin(t) for t in src.tones])
+
+    def setup(e):
+        e.clients_create(nc, n, cfg.audio_sps)
+        for i, c in enumerate(specs):
+            e.client_open(i, c.l, c.mid, c.r, c.mode)
+
+    # reference-shaped per-frame calls
+    a = make_engine(cfg)
+    setup(a)
+    ring = [a.malloc(cfg.hop_floats) for _ in range(3)]
+    want_pcm, want_pyr = [], []
+    ring[0][:] = hops[0]
+    for f in range(F * nblocks):
+        ring[(f + 1) % 3][:] = hops[f + 1]
+        (a.load_real_input if is_real else a.load_complex_input)(ring[f % 3], ring[(f + 1) % 3])
+        a.execute()
+        pcm, pwr, valid = a.clients_execute(f)
+        assert valid[:nc].all()
+        want_pcm.append(pcm.copy())
+        want_pyr.append(a.get_quantized_buffer().copy())
+    a.close()
+
+    # pipelined blocks
+    b = make_engine(cfg)
+    b.set_hop_ring(2 * F + 2)
+    b.set_batch_frames(F)
+    b.set_pipeline(2)
+    setup(b)
+    sets = []
+    for _ in range(2):
+        sets.append(dict(halves=[b.malloc(cfg.hop_floats) for _ in range(F)], pcm=b.pinned(4 * F * nc * h, np.int32),
+                         pwr=b.pinned(4 * F * nc, np.float32), valid=b.pinned(F * nc, np.uint8),
+                         pyr=b.pinned(F * b.pyramid_bytes, np.int8)))
+    prime = b.malloc(cfg.hop_floats)
+    prime[:] = hops[0]
+    b.stream_prime(prime)
+    got_pcm, got_pyr = [], []
+
+    def collect(st):
+        got_pcm.extend(st["pcm"].reshape(F, nc, h).copy())
+        got_pyr.extend(st["pyr"].reshape(F, -1).copy())
+
+    for k in range(nblocks):
+        st = sets[k & 1]
+        if k >= 2:
+            b.wait_block()
+            collect(sets[k & 1])
+        for f in range(F):
+            st["halves"][f][:] = hops[1 + k * F + f]
+        b.submit_block(st["halves"], k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
+    # drain in submission order
+    pending = list(range(max(0, nblocks - 2), nblocks))
+    for k in pending:
+        b.wait_block()
+        collect(sets[k & 1])
+    b.close()
+    assert len(got_pcm) == F * nblocks
+    for f in range(F * nblocks):
+        assert np.array_equal(got_pyr[f], want_pyr[f]), f"frame {f}: pyramid differs"
+        assert np.array_equal(got_pcm[f], want_pcm[f][:nc]), f"frame {f}: PCM differs"
