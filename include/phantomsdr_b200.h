@@ -115,6 +115,7 @@ int b200_execute(b200_engine *e);
                                    registers, upper levels in a small kernel; 2 = pass 2 stores |X|^2, quantiser + pyramid in
                                    one streaming kernel; 0 = the pyramid kernel re-reads the spectrum */
 #define B200_OPT_TMA 6           /* 1 (default): persistent TMA-fed FFT passes where available (2^20-point transforms) */
+#define B200_OPT_TAIL_PIPELINE 7 /* 1 (default): frame-skewed software pipeline for the DC/AGC tails when >= 4 frames per call */
 #define B200_OPT_STAGE_MASK 4    /* profiling aid: bit0 = FFT pass 1, bit1 = pass 2, bit2 = pyramid; default 7 */
 int b200_set_option(b200_engine *e, int option, int value);
 

@@ -134,6 +134,7 @@ struct b200_engine {
     int opt_stage_mask = 7;
     int opt_fused_pyramid = 1;
     int opt_tma = 1;
+    int opt_tail_pipe = 1;
     bool tma_ok = false;
     int num_sms = 148;
     CUtensorMap ring_map{}, window_map{};
@@ -596,8 +597,31 @@ template <int KB> int launch_tail_kb(b200_engine *e, const ClientLaunch &cl) {
     CU(cudaGetLastError());
     return 0;
 }
+template <int KB> int launch_tail_pipe_kb(b200_engine *e, const ClientLaunch &cl) {
+    const size_t smem = tail_pipe_smem(e->ca.h, e->ca.D);
+    if (cl.nactive == 0) {  // preparation call from clients_create
+        CU(cudaFuncSetAttribute(client_tail_pipe_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return 0;
+    }
+    const int blocks = (cl.nactive + kPipeCpb - 1) / kPipeCpb;
+    client_tail_pipe_kernel<KB><<<blocks, kPipeThreads, smem, e->client_stream()>>>(e->ca, cl);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+bool tail_pipe_ok(const b200_engine *e) {
+    // frame-skewed pipeline: DC delay state kept as <= 4 values per lane, tiles must fit, and batches only
+    return e->opt_tail_pipe && e->ca.D <= 128 && tail_pipe_smem(e->ca.h, e->ca.D) <= 200 * 1024 && e->batch <= kPipeMaxFrames;
+}
 int launch_tail(b200_engine *e, const ClientLaunch &cl) {
     const int kb = (e->ca.h + 31) / 32;
+    if (tail_pipe_ok(e) && (cl.nactive == 0 || cl.nframes >= 4)) {
+        int rc;
+        if (kb <= 6) rc = launch_tail_pipe_kb<6>(e, cl);
+        else if (kb <= 9) rc = launch_tail_pipe_kb<9>(e, cl);
+        else rc = launch_tail_pipe_kb<0>(e, cl);
+        if (rc || cl.nactive != 0) return rc;
+    }
     if (kb <= 2) return launch_tail_kb<2>(e, cl);
     if (kb <= 4) return launch_tail_kb<4>(e, cl);
     if (kb <= 6) return launch_tail_kb<6>(e, cl);
@@ -849,6 +873,7 @@ int b200_set_option(b200_engine *e, int option, int value) {
         e->opt_fused_pyramid = value;
         return 0;
     case B200_OPT_TMA: e->opt_tma = value ? 1 : 0; return 0;
+    case B200_OPT_TAIL_PIPELINE: e->opt_tail_pipe = value ? 1 : 0; return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
         if (value != e->in_format) {

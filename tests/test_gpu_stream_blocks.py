@@ -78,3 +78,46 @@ def test_block_streaming_equals_per_frame_calls(gpu_required, is_real):
     for f in range(F * nblocks):
         assert np.array_equal(got_pyr[f], want_pyr[f]), f"frame {f}: pyramid differs"
         assert np.array_equal(got_pcm[f], want_pcm[f][:nc]), f"frame {f}: PCM differs"
+
+
+def test_pipelined_tail_equals_phase_tail(gpu_required):
+    """The frame-skewed tail pipeline (default for batches >= 4 frames) must be bit-identical to the per-phase tail
+    kernel, including AGC warm-up (zeros until the look-ahead fills), a mode switch (AGC reset) and batches that
+    straddle the moment the look-ahead fills."""
+    from phantomsdr_b200.backend import OPT_TAIL_PIPELINE
+    import torch
+
+    cfg = SpectrumConfig(sps=4_370_000, fft_size=1 << 17)
+    n, h = cfg.audio_fft_size, cfg.audio_fft_size // 2
+    F, nblocks, nc = 8, 5, 19
+    src = SignalSource(cfg, seed=33)
+    specs = make_clients(cfg, nc, modes=(USB, LSB, AM, FM), tones=[src.display_bin(t) for t in src.tones])
+    hops = np.stack([hop_as_floats(src.next_hop()) for _ in range(F * nblocks + 1)])
+    results = []
+    for pipe in (0, 1):
+        e = make_engine(cfg)
+        e.set_hop_ring(F * nblocks + 1)
+        e.set_batch_frames(F)
+        e.set_option(OPT_TAIL_PIPELINE, pipe)
+        e.clients_create(nc + 2, n, cfg.audio_sps)
+        for i, c in enumerate(specs):
+            e.client_open(i, c.l, c.mid, c.r, c.mode)
+        ring = torch.as_tensor(e.device_hop_ring(F * nblocks + 1), device="cuda")
+        ring.copy_(torch.from_numpy(hops))
+        torch.cuda.synchronize()
+        out = []
+        for k in range(nblocks):
+            if k == 2:
+                e.client_set_demodulation(3, AM)   # AGC reset in the middle of the stream
+                e.client_set_demodulation(4, USB)
+            e.execute_device(k * F, F)
+            e.clients_execute_device(k * F, F)
+            for f in range(F):
+                pcm, pwr, valid = e.clients_fetch(f)
+                out.append((pcm.copy(), valid.copy()))
+        results.append(out)
+        e.close()
+    for f, ((pa, va), (pb, vb)) in enumerate(zip(*results)):
+        assert np.array_equal(va, vb), f"frame {f}: valid flags differ"
+        assert np.array_equal(pa, pb), f"frame {f}: PCM differs at clients {np.flatnonzero((pa != pb).any(axis=1))[:8]}"
+    assert any(p.any() for p, _ in results[1][20:]), "AGC never opened: test is vacuous"
