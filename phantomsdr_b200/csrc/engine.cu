@@ -110,6 +110,7 @@ struct b200_engine {
 
     float *d_window = nullptr;
     float2 *d_Y = nullptr, *d_Z = nullptr, *d_spec = nullptr, *spec_bound = nullptr;
+    float2 *d_spec_raw = nullptr;  // d_spec = d_spec_raw + 15: bin 1 (first bin of every IQ tile run) sits on a 128-byte line
     int8_t *d_quant = nullptr;
     float *d_ptop = nullptr;
     float *d_pscratch = nullptr;
@@ -132,7 +133,7 @@ struct b200_engine {
     int opt_reload_both = 0;
     int opt_mirror = 3;
     int opt_stage_mask = 7;
-    int opt_fused_pyramid = 1;
+    int opt_fused_pyramid = 2;
     int opt_tma = 1;
     int opt_tail_pipe = 1;
     bool tma_ok = false;
@@ -427,15 +428,18 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     q.npeers = e->is_real ? e->npeers : 0;
     for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i];
     if (e->levels > q.base_level) {
-        dim3 grid((unsigned)((e->R >> q.base_level) / 1024), frames);
-        if (e->is_real) pyramid_kernel<PYR_R2C><<<grid, 256, 0, e->stream>>>(q);
-        else if (fuse == 1) pyramid_kernel<PYR_SCRATCH><<<grid, 256, 0, e->stream>>>(q);
-        else if (fuse == 2) pyramid_kernel<PYR_POWER><<<grid, 256, 0, e->stream>>>(q);
-        else pyramid_kernel<PYR_SPEC><<<grid, 256, 0, e->stream>>>(q);
+        // 16 entries per thread for the full-resolution inputs, 4 for the small per-tile sums of mode 1
+        const int per = (fuse == 1) ? 4 : 16;
+        dim3 grid((unsigned)((e->R >> q.base_level) / (256 * per)), frames);
+        if (e->is_real) pyramid_kernel<PYR_R2C, 16><<<grid, 256, 0, e->stream>>>(q);
+        else if (fuse == 1) pyramid_kernel<PYR_SCRATCH, 4><<<grid, 256, 0, e->stream>>>(q);
+        else if (fuse == 2) pyramid_kernel<PYR_POWER, 16><<<grid, 256, 0, e->stream>>>(q);
+        else pyramid_kernel<PYR_SPEC, 16><<<grid, 256, 0, e->stream>>>(q);
         e->launches++;
         CU(cudaGetLastError());
-        if (e->levels - q.base_level > 11) {
-            pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q, q.base_level);
+        const int levels_done = (per == 16 ? 4 : 2) + 9;
+        if (e->levels - q.base_level > levels_done) {
+            pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q, q.base_level, levels_done);
             e->launches++;
             CU(cudaGetLastError());
         }
@@ -467,7 +471,7 @@ int plan_common(b200_engine *e, bool is_real) {
     if (e->levels < 1) return fail(B200_EINVAL, "downsample_levels must be >= 1");
     if ((e->R >> (e->levels - 1)) < 1) return fail(B200_EINVAL, "too many downsample levels for %zu bins", e->R);
     e->hop_samples = is_real ? e->size / 2 : e->size;  // scalar samples per hop
-    e->spec_stride = is_real ? (e->size / 2 + 8) : (e->size + ((e->additional + 7) & ~(size_t)7) + 8);
+    e->spec_stride = is_real ? (e->size / 2 + 16) : (e->size + ((e->additional + 15) & ~(size_t)15) + 16);
     e->pyr_bytes = 0;
     for (int i = 0; i < e->levels; i++) e->pyr_bytes += e->R >> i;
     e->pyr_stride = (e->pyr_bytes + 255) & ~(size_t)255;
@@ -507,7 +511,8 @@ int plan_common(b200_engine *e, bool is_real) {
 int alloc_batch(b200_engine *e, int frames) {
     if (e->d_Y) cudaFree(e->d_Y);
     if (e->d_Z) cudaFree(e->d_Z);
-    if (e->d_spec) cudaFree(e->d_spec);
+    if (e->d_spec_raw) cudaFree(e->d_spec_raw);
+    e->d_spec_raw = nullptr;
     if (e->d_quant) cudaFree(e->d_quant);
     if (e->d_ptop) cudaFree(e->d_ptop);
     if (e->d_pscratch) cudaFree(e->d_pscratch);
@@ -517,8 +522,11 @@ int alloc_batch(b200_engine *e, int frames) {
     e->d_ptop = nullptr;
     CU(cudaMalloc(&e->d_Y, sizeof(float2) * e->M * frames));
     if (e->is_real) CU(cudaMalloc(&e->d_Z, sizeof(float2) * e->M * frames));
-    CU(cudaMalloc(&e->d_spec, sizeof(float2) * e->spec_stride * frames * e->banks));
-    CU(cudaMemset(e->d_spec, 0, sizeof(float2) * e->spec_stride * frames * e->banks));
+    // IQ bins are stored in runs k = 8m+1 .. 8m+8 (display shift, fft_impl.cpp:148-160): offsetting the buffer by 15
+    // elements makes every run start on a 64-byte boundary, so pass 2 writes whole sectors
+    CU(cudaMalloc(&e->d_spec_raw, sizeof(float2) * (e->spec_stride * frames * e->banks + 16)));
+    CU(cudaMemset(e->d_spec_raw, 0, sizeof(float2) * (e->spec_stride * frames * e->banks + 16)));
+    e->d_spec = e->d_spec_raw + 15;
     CU(cudaMalloc(&e->d_quant, e->pyr_stride * frames * e->banks));
     CU(cudaMemset(e->d_quant, 0, e->pyr_stride * frames * e->banks));
     e->cur_bank = 0;
@@ -761,7 +769,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec, e->d_quant, e->d_ptop, e->d_pscratch, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
+    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,

@@ -338,23 +338,26 @@ struct PyrParams {
     float2 *peers[kMaxPeers];
 };
 
-// grid ((R >> base_level)/1024, frames), block 256: each thread owns 4 consecutive entries of the base level
-// and the block reduces up to ten more levels (pairwise sums, src/fft_impl.cpp:45-61,162-172).
-template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+// grid ((R >> base_level) / (256*PER), frames), block 256: each thread owns PER (4 or 16) consecutive entries of the
+// base level; the block then reduces log2(PER) levels in registers, five with warp shuffles and three through
+// shared memory (pairwise sums, src/fft_impl.cpp:45-61,162-172) - log2(PER) + 8 levels above the base in all.
+template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+    static_assert(PER == 4 || PER == 16, "PER must be 4 or 16");
+    constexpr int LP = (PER == 16) ? 4 : 2;  // levels reduced in registers
     __shared__ float warp_sum_s[8];
     const int tid = threadIdx.x;
     const int frame = blockIdx.y;
     const size_t R = (size_t)1 << p.log2R;
     const int B = (MODE == PYR_SCRATCH) ? p.base_level : 0;
-    const size_t d0 = (size_t)blockIdx.x * 1024 + 4 * tid;  // index at level B
+    const size_t d0 = ((size_t)blockIdx.x * 256 + tid) * PER;  // index at level B
     int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
 
-    float pw[4];
+    float pw[PER];
     if constexpr (MODE == PYR_SPEC) {
         // display bin d <-> FFT bin (d + R/2 + 1) mod R   (src/fft_impl.cpp:148-160)
         const float2 *spec = p.spec + (size_t)frame * p.spec_stride;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < PER; i++) {
             const size_t k = (d0 + i + (R >> 1) + 1) & (R - 1);
             const float2 x = spec[k];
             pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
@@ -364,7 +367,7 @@ template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const 
         float2 *spec = p.spec + (size_t)frame * p.spec_stride;
         const float2 *Z = p.Z + (size_t)frame * R;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < PER; i++) {
             const size_t k = d0 + i;
             const float2 a = Z[k];
             const float2 b = Z[(R - k) & (R - 1)];
@@ -391,15 +394,19 @@ template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const 
         const int N1 = p.ntiles, N2 = p.N2;  // (ntiles carries N1 in this mode)
         const size_t u1 = d0 & (size_t)(N1 - 1), d2 = d0 / N1;
         const size_t u2 = (d2 + (N2 >> 1)) & (size_t)(N2 - 1);
-        const float4 f = *reinterpret_cast<const float4 *>(p.pscratch + (size_t)frame * R + u2 * N1 + u1);
-        pw[0] = f.x;
-        pw[1] = f.y;
-        pw[2] = f.z;
-        pw[3] = f.w;
+        const float4 *src = reinterpret_cast<const float4 *>(p.pscratch + (size_t)frame * R + u2 * N1 + u1);
+#pragma unroll
+        for (int i = 0; i < PER / 4; i++) {
+            const float4 f = src[i];
+            pw[4 * i] = f.x;
+            pw[4 * i + 1] = f.y;
+            pw[4 * i + 2] = f.z;
+            pw[4 * i + 3] = f.w;
+        }
     } else {
         const float *scr = p.pscratch + (size_t)frame * p.ntiles * p.N2;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < PER; i++) {
             const size_t idx = d0 + i;
             const size_t tile = idx % p.ntiles, d2 = idx / p.ntiles;
             pw[i] = scr[tile * p.N2 + d2];
@@ -411,50 +418,54 @@ template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const 
     for (int i = 0; i < B; i++) lvl_off += R >> i;
     const size_t RB_ = R >> B;   // entries at the base level
     if (L <= 0) return;
-    {
-        unsigned packed = 0;
+    // relative levels 0 .. LP in registers: level lv has PER >> lv values per thread, stored as one word/vector
+    static_for<LP + 1>([&](auto lvc) {
+        constexpr int lv = decltype(lvc)::value;
+        constexpr int CNT = PER >> lv;
+        if (lv < L) {
+            unsigned w[(CNT + 3) / 4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) packed |= (unsigned)quantize_dev(pw[i], off) << (8 * i);
-        *reinterpret_cast<unsigned *>(quant + lvl_off + d0) = packed;
-    }
-    lvl_off += RB_;
-    if (L > 1) {
-        const float s0 = __fadd_rn(pw[0], pw[1]), s1 = __fadd_rn(pw[2], pw[3]);
-        const unsigned short pk = (unsigned short)(quantize_dev(s0, off - 1) | (quantize_dev(s1, off - 1) << 8));
-        *reinterpret_cast<unsigned short *>(quant + lvl_off + (d0 >> 1)) = pk;
-        lvl_off += RB_ >> 1;
-        float s = __fadd_rn(s0, s1);
-        if (L > 2) {
-            quant[lvl_off + (d0 >> 2)] = (int8_t)quantize_dev(s, off - 2);
-            lvl_off += RB_ >> 2;
-            // relative levels 3..7 inside the warp
-            const int lane = tid & 31;
+            for (int i = 0; i < (CNT + 3) / 4; i++) w[i] = 0;
 #pragma unroll
-            for (int lv = 3; lv <= 7; lv++) {
-                if (lv < L) {
-                    s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1 << (lv - 3)));
-                    if ((lane & ((1 << (lv - 2)) - 1)) == 0)
-                        quant[lvl_off + (d0 >> lv)] = (int8_t)quantize_dev(s, off - lv);
-                    lvl_off += RB_ >> lv;
-                }
+            for (int i = 0; i < CNT; i++) w[i / 4] |= (unsigned)quantize_dev(pw[i], off - lv) << (8 * (i % 4));
+            store_packed<CNT>(quant + lvl_off + (d0 >> lv), w);
+        }
+        lvl_off += RB_ >> lv;
+        if constexpr (CNT > 1) {
+#pragma unroll
+            for (int i = 0; i < CNT / 2; i++) pw[i] = __fadd_rn(pw[2 * i], pw[2 * i + 1]);
+        }
+    });
+    // pw[0] now holds the thread's level-LP sum (already written above)
+    if (L > LP + 1) {
+        float s = pw[0];
+        const int lane = tid & 31;
+#pragma unroll
+        for (int k = 1; k <= 5; k++) {  // relative levels LP+1 .. LP+5 inside the warp
+            const int lv = LP + k;
+            if (lv < L) {
+                s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1 << (k - 1)));
+                if ((lane & ((1 << k) - 1)) == 0) quant[lvl_off + (d0 >> lv)] = (int8_t)quantize_dev(s, off - lv);
+                lvl_off += RB_ >> lv;
             }
-            if (L > 8) {
-                if (lane == 0) warp_sum_s[tid >> 5] = s;
-                __syncthreads();
-                if (tid < 8) {
-                    float w = warp_sum_s[tid];
-                    const size_t b0 = (size_t)blockIdx.x * 1024;
+        }
+        if (L > LP + 6) {
+            if (lane == 0) warp_sum_s[tid >> 5] = s;
+            __syncthreads();
+            if (tid < 8) {
+                float w = warp_sum_s[tid];
+                const size_t b0 = (size_t)blockIdx.x * 256 * PER;
 #pragma unroll
-                    for (int lv = 8; lv <= 10; lv++) {
-                        if (lv < L) {
-                            w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (lv - 8)));
-                            if ((tid & ((1 << (lv - 7)) - 1)) == 0)
-                                quant[lvl_off + ((b0 + 128 * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
-                            lvl_off += RB_ >> lv;
-                        }
+                for (int k = 1; k <= 3; k++) {  // relative levels LP+6 .. LP+8 across the eight warps
+                    const int lv = LP + 5 + k;
+                    if (lv < L) {
+                        w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (k - 1)));
+                        if ((tid & ((1 << k) - 1)) == 0)
+                            quant[lvl_off + ((b0 + (size_t)32 * PER * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
+                        lvl_off += RB_ >> lv;
                     }
-                    if (L > 11 && tid == 0) p.ptop[(size_t)frame * (RB_ >> 10) + blockIdx.x] = w;
                 }
+                if (L > LP + 9 && tid == 0) p.ptop[(size_t)frame * (RB_ / (256 * PER)) + blockIdx.x] = w;
             }
         }
     }
@@ -462,11 +473,12 @@ template <int MODE> __global__ void __launch_bounds__(256) pyramid_kernel(const 
 
 // more than ten levels above the base (only for very deep pyramids): one block per frame, pairwise tree over
 // the sums left in ptop. Tiny.
-__global__ void pyramid_tail_kernel(const PyrParams p, int base_level) {
+__global__ void pyramid_tail_kernel(const PyrParams p, int base_level, int levels_done) {
+    // levels_done = relative levels already produced by pyramid_kernel (log2(PER) + 9); ptop holds the sums of the last one
     const int frame = blockIdx.x;
     const size_t R = (size_t)1 << p.log2R;
-    const int first = base_level + 11;
-    size_t n = R >> (base_level + 10);
+    const int first = base_level + levels_done;
+    size_t n = R >> (first - 1);
     float *buf = p.ptop + (size_t)frame * n;
     int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
     size_t lvl_off = 0;

@@ -36,9 +36,9 @@ def t(mask, reps=10):
     return a.elapsed_time(b) * 1e3 / (reps * H)
 
 
-for name, opts in (("tma fused(1)", {}), ("tma power(2)", {OPT_FUSED_PYRAMID: 2}), ("tma unfused(0)", {OPT_FUSED_PYRAMID: 0}),
-                   ("no tma fused", {OPT_TMA: 0})):
-    eng.set_option(OPT_FUSED_PYRAMID, 1)
+for name, opts in (("tma power(2)", {}), ("tma fused(1)", {OPT_FUSED_PYRAMID: 1}), ("tma unfused(0)", {OPT_FUSED_PYRAMID: 0}),
+                   ("no tma power", {OPT_TMA: 0})):
+    eng.set_option(OPT_FUSED_PYRAMID, 2)
     eng.set_option(OPT_TMA, 1)
     for k, v in opts.items():
         eng.set_option(k, v)
