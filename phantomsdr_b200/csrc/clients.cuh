@@ -36,6 +36,9 @@ struct ClientArrays {
     float attack, release, desired;
     int nstages;
     int radix[kMaxStages];
+    unsigned mul_s[kMaxStages];      // floor(2^32 / s) + 1 for the stride s of each stage (t / s = umulhi(t, mul))
+    unsigned mul_items[kMaxStages];  // same for items = n / radix
+    unsigned mul_n;                  // same for n
     const float2 *Wn;    // exp(+2*pi*i*k/n), k < n
     // per-slot parameters and state (device)
     ClientSlot *slots;
@@ -68,6 +71,7 @@ struct ClientLaunch {
     int is_real;
     const int *order;    // active slots in (l, r) order
     int nactive;
+    int fchunk;          // demod kernel: frames whose inverse FFTs are batched in shared memory at once
     int cpb;             // tail kernel: clients per block
     long long *prof;     // optional: per-phase SM clock totals of block 0 (profiling aid), 8 entries
 };
@@ -78,14 +82,19 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// One Stockham stage of radix R (sign +1):  x[t + j*items] -> y[q + s*(R*p + r)], t = p*s + q.
-// The whole CTA (nthr threads) shares the work.
+// One Stockham stage of radix R (sign +1) over `nf` independent transforms stored back to back:
+//   x[t + j*items] -> y[q + s*(R*p + r)],  t = p*s + q,  items = n / R.
+// The whole CTA shares the nf * items butterflies; divisions are multiply-high with host-made constants.
 template <int R>
-__device__ __forceinline__ void ifft_stage_fixed(const float2 *x, float2 *y, int n, int s, const float2 *Wn, int tid,
-                                                 int nthr) {
+__device__ __forceinline__ void ifft_stage_fixed(const float2 *xb, float2 *yb, int n, int s, unsigned mul_s, unsigned mul_items,
+                                                 int nf, const float2 *Wn, int tid, int nthr) {
     const int items = n / R;
-    for (int t = tid; t < items; t += nthr) {
-        const int p = t / s, q = t - p * s;
+    for (int T = tid; T < nf * items; T += nthr) {
+        const int fr = __umulhi((unsigned)T, mul_items);
+        const int t = T - fr * items;
+        const int p = (s == 1) ? t : (int)__umulhi((unsigned)t, mul_s), q = t - p * s;
+        const float2 *x = xb + fr * n;
+        float2 *y = yb + fr * n;
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; j++) a[j] = x[t + j * items];
@@ -134,13 +143,16 @@ __device__ __forceinline__ void ifft_stage_fixed(const float2 *x, float2 *y, int
 }
 
 // generic (prime) radix: one thread per OUTPUT, R complex MACs each
-__device__ __forceinline__ void ifft_stage_generic(const float2 *x, float2 *y, int n, int s, int R, const float2 *Wn,
-                                                   int tid, int nthr) {
+__device__ __forceinline__ void ifft_stage_generic(const float2 *xb, float2 *yb, int n, int s, int R, unsigned mul_s,
+                                                   unsigned mul_n, int nf, const float2 *Wn, int tid, int nthr) {
     const int items = n / R;
     const int step = n / R;  // W_R = Wn[n/R]
-    for (int o = tid; o < n; o += nthr) {
+    for (int O = tid; O < nf * n; O += nthr) {
+        const int fr = __umulhi((unsigned)O, mul_n);
+        const int o = O - fr * n;
         const int t = o / R, r = o - t * R;
-        const int p = t / s, q = t - p * s;
+        const int p = (s == 1) ? t : (int)__umulhi((unsigned)t, mul_s), q = t - p * s;
+        const float2 *x = xb + fr * n;
         float2 acc = x[t];
         int idx = 0;
         for (int j = 1; j < R; j++) {
@@ -152,21 +164,24 @@ __device__ __forceinline__ void ifft_stage_generic(const float2 *x, float2 *y, i
             acc.y += v.x * w.y + v.y * w.x;
         }
         if (r) acc = cmul(acc, __ldg(Wn + p * s * r));
-        y[q + s * (R * p + r)] = acc;
+        yb[fr * n + q + s * (R * p + r)] = acc;
     }
 }
 
-// grid: one CTA per active client, TPB threads; dynamic smem 2n float2
+// grid: one CTA per active client, TPB threads; dynamic smem 2 * fchunk * n float2. The inverse FFTs of up to
+// `fchunk` consecutive frames are independent, so they are gathered and transformed together (full lanes, one
+// barrier per stage for the whole chunk); only the overlap-add / demodulation walks the frames in order.
 template <int TPB>
 __global__ void __launch_bounds__(TPB) client_demod_kernel(const ClientArrays ca, const ClientLaunch cl) {
     extern __shared__ float2 smem_c[];
-    __shared__ float s_red[TPB / 32];
+    __shared__ float s_pw[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ci = blockIdx.x;
     const int slot = cl.order[ci];
     const int n = ca.n, h = ca.h;
+    const int FC = cl.fchunk;
     float2 *bufX = smem_c;
-    float2 *bufY = bufX + n;
+    float2 *bufY = bufX + (size_t)FC * n;
     const ClientSlot cs = ca.slots[slot];
     const size_t R = cl.is_real ? cl.fft_size / 2 : cl.fft_size;
     const size_t base_idx = cl.is_real ? 0 : cl.fft_size / 2 + 1;
@@ -192,115 +207,127 @@ __global__ void __launch_bounds__(TPB) client_demod_kernel(const ClientArrays ca
         __syncthreads();
     }
 
-    for (int f = 0; f < cl.nframes; f++) {
-        const unsigned long long frame_num = cl.frame_num0 + f;
-        const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
-        for (int i = tid; i < n; i += TPB) bufX[i] = make_float2(0.f, 0.f);
-        __syncthreads();
-        // gather + placement + slice power (signal.cpp:117-198)
-        float pw = 0.f;
-        for (int i = tid; i < len; i += TPB) {
-            const float2 v = buf[i];
-            pw += v.x * v.x + v.y * v.y;
+    for (int f0 = 0; f0 < cl.nframes; f0 += FC) {
+        const int nf = min(FC, cl.nframes - f0);
+        // ---- placement of the slice into the IFFT input (signal.cpp:125-198), all frames of the chunk at once:
+        //      every input position looks up the bin that the reference copies there (or stays zero) ----
+        for (int idx = tid; idx < nf * n; idx += TPB) {
+            const int fr = __umulhi((unsigned)idx, ca.mul_n);
+            const int kk = idx - fr * n;
+            const float2 *buf = cl.spec + (size_t)(f0 + fr) * cl.spec_stride + off;
+            float2 v = make_float2(0.f, 0.f);
             if (mode == MODE_USB || mode == MODE_LSB) {
-                const int kk = (mode == MODE_USB) ? (i - audio_m) : (audio_m - i);
-                if (kk >= 0 && kk <= n / 2) {
-                    if (kk == 0 || kk == n / 2) {
-                        bufX[kk] = make_float2(v.x, 0.f);  // c2r ignores Im of DC / Nyquist
-                    } else {
-                        bufX[kk] = v;
-                        bufX[n - kk] = make_float2(v.x, -v.y);
-                    }
+                // c2r reads bins 0..n/2 of its input; the other half is the Hermitian mirror
+                const int k2 = (kk <= n / 2) ? kk : n - kk;
+                const int i = (mode == MODE_USB) ? (audio_m + k2) : (audio_m - k2);
+                if (i >= 0 && i < len) {
+                    v = buf[i];
+                    if (k2 == 0 || k2 == n / 2) v.y = 0.f;  // c2r ignores Im of DC / Nyquist
+                    else if (kk > n / 2) v.y = -v.y;
                 }
             } else {
-                const int d = i - audio_m;
-                if (d >= 0 && d < n / 2) bufX[d] = v;
-                else if (d < 0 && d >= -(n / 2) + 1) bufX[n + d] = v;
+                const int d = (kk < n / 2) ? kk : kk - n;  // positive bins [0, n/2), negative [-n/2+1, -1]; kk = n/2 stays 0
+                const int i = audio_m + d;
+                if (kk != n / 2 && i >= 0 && i < len) v = buf[i];
             }
+            bufX[idx] = v;
         }
-        pw = warp_sum(pw);
-        if (lane == 0) s_red[warp] = pw;
+        // slice power of every frame (signal.cpp:117-119): one warp per frame
+        for (int fr = warp; fr < nf; fr += TPB / 32) {
+            const float2 *buf = cl.spec + (size_t)(f0 + fr) * cl.spec_stride + off;
+            float pw = 0.f;
+            for (int i = lane; i < len; i += 32) {
+                const float2 v = buf[i];
+                pw += v.x * v.x + v.y * v.y;
+            }
+            pw = warp_sum(pw);
+            if (lane == 0) s_pw[fr] = pw;
+        }
         __syncthreads();
-        // inverse FFT, unnormalised (signal.cpp:138,154,214)
-        float2 *x = bufX, *y = bufY;
+        // ---- inverse FFTs, unnormalised (signal.cpp:138,154,214) ----
+        float2 *xb = bufX, *yb = bufY;
         int s = 1;
         for (int st = 0; st < ca.nstages; st++) {
             const int Rr = ca.radix[st];
-            if (Rr == 4) ifft_stage_fixed<4>(x, y, n, s, ca.Wn, tid, TPB);
-            else if (Rr == 2) ifft_stage_fixed<2>(x, y, n, s, ca.Wn, tid, TPB);
-            else if (Rr == 3) ifft_stage_fixed<3>(x, y, n, s, ca.Wn, tid, TPB);
-            else if (Rr == 5) ifft_stage_fixed<5>(x, y, n, s, ca.Wn, tid, TPB);
-            else ifft_stage_generic(x, y, n, s, Rr, ca.Wn, tid, TPB);
+            if (Rr == 4) ifft_stage_fixed<4>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], nf, ca.Wn, tid, TPB);
+            else if (Rr == 2) ifft_stage_fixed<2>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], nf, ca.Wn, tid, TPB);
+            else if (Rr == 3) ifft_stage_fixed<3>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], nf, ca.Wn, tid, TPB);
+            else if (Rr == 5) ifft_stage_fixed<5>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], nf, ca.Wn, tid, TPB);
+            else ifft_stage_generic(xb, yb, n, s, Rr, ca.mul_s[st], ca.mul_n, nf, ca.Wn, tid, TPB);
             s *= Rr;
-            float2 *t = x;
-            x = y;
-            y = t;
+            float2 *t = xb;
+            xb = yb;
+            yb = t;
             __syncthreads();
         }
-        // x holds the time-domain result
-        const int m_idx = cs.m_floor;
-        const bool negate = (frame_num & 1ull) && (((m_idx % 2 == 0) && !cl.is_real) || ((m_idx % 2 == 1) && cl.is_real));
-        const float sg = negate ? -1.f : 1.f;
-        float *audio = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
-        int nan_seen = 0;
-        if (mode == MODE_USB || mode == MODE_LSB) {
-            // signal.cpp:155-172: (LSB: time reverse), parity negate, overlap-add
-            for (int t = tid; t < h; t += TPB) {
-                const float lo = (mode == MODE_USB) ? x[t].x : x[n - 1 - t].x;
-                const float o = __fadd_rn(sg * lo, real_prev[t]);
-                nan_seen |= (o != o);
-                audio[t] = o;
-            }
-            nan_seen = __syncthreads_or(nan_seen);
-            float *dst = nan_seen ? real_hi : real_prev;  // signal.cpp:266-275: prev only advances on a sent frame
-            for (int t = tid; t < h; t += TPB) {
-                const float hi = (mode == MODE_USB) ? x[h + t].x : x[n - 1 - (h + t)].x;
-                dst[t] = sg * hi;
-            }
-            if (tid == 0) ca.hi_diverged[slot] = nan_seen ? 1 : 0;
-        } else {
-            // signal.cpp:200-263
-            const float2 prev_last = ca.bb_last[slot];
-            float2 *bb = y;  // assemble the overlapped first half in the free buffer
-            for (int t = tid; t < h; t += TPB) {
-                const float2 lo = x[t], old = bb_hi[t];
-                bb[t] = make_float2(__fadd_rn(sg * lo.x, old.x), __fadd_rn(sg * lo.y, old.y));
-            }
-            __syncthreads();
-            for (int t = tid; t < h; t += TPB) {
-                const float2 hi = x[h + t];
-                bb_hi[t] = make_float2(sg * hi.x, sg * hi.y);
-                const float2 b = bb[t];
-                float o;
-                if (mode == MODE_AM) {
-                    o = __fsqrt_rn(__fadd_rn(__fmul_rn(b.x, b.x), __fmul_rn(b.y, b.y)));  // dsp.cpp:116-126
-                } else {
-                    const float2 pv = (t == 0) ? prev_last : bb[t - 1];
-                    const float c = pv.x, d = -pv.y;  // buf[i] * conj(prev), dsp.cpp:27-35
-                    const float re = __fsub_rn(__fmul_rn(b.x, c), __fmul_rn(b.y, d));
-                    const float im = __fadd_rn(__fmul_rn(b.x, d), __fmul_rn(b.y, c));
-                    o = atan2f(im, re);
+        // ---- frames in order: parity sign flip, overlap-add with the carried state, demodulation ----
+        for (int fr = 0; fr < nf; fr++) {
+            const int f = f0 + fr;
+            const float2 *x = xb + (size_t)fr * n;  // time-domain result of this frame
+            float2 *y = yb + (size_t)fr * n;        // free scratch of this frame
+            const unsigned long long frame_num = cl.frame_num0 + f;
+            const int m_idx = cs.m_floor;
+            const bool negate =
+                (frame_num & 1ull) && (((m_idx % 2 == 0) && !cl.is_real) || ((m_idx % 2 == 1) && cl.is_real));
+            const float sg = negate ? -1.f : 1.f;
+            float *audio = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
+            int nan_seen = 0;
+            if (mode == MODE_USB || mode == MODE_LSB) {
+                // signal.cpp:155-172: (LSB: time reverse), parity negate, overlap-add
+                for (int t = tid; t < h; t += TPB) {
+                    const float lo = (mode == MODE_USB) ? x[t].x : x[n - 1 - t].x;
+                    const float o = __fadd_rn(sg * lo, real_prev[t]);
+                    nan_seen |= (o != o);
+                    audio[t] = o;
                 }
-                nan_seen |= (o != o);
-                audio[t] = o;
-            }
-            nan_seen = __syncthreads_or(nan_seen);
-            if (tid == 0) ca.bb_last[slot] = bb[h - 1];
-            if (!nan_seen && ca.hi_diverged[slot]) {
-                // audio_real_prev <- audio_real[n/2..n) left behind by a NaN-dropped SSB frame
-                for (int t = tid; t < h; t += TPB) real_prev[t] = real_hi[t];
+                nan_seen = __syncthreads_or(nan_seen);
+                float *dst = nan_seen ? real_hi : real_prev;  // signal.cpp:266-275: prev only advances on a sent frame
+                for (int t = tid; t < h; t += TPB) {
+                    const float hi = (mode == MODE_USB) ? x[h + t].x : x[n - 1 - (h + t)].x;
+                    dst[t] = sg * hi;
+                }
+                if (tid == 0) ca.hi_diverged[slot] = nan_seen ? 1 : 0;
+            } else {
+                // signal.cpp:200-263
+                const float2 prev_last = ca.bb_last[slot];
+                float2 *bb = y;  // assemble the overlapped first half in the free buffer
+                for (int t = tid; t < h; t += TPB) {
+                    const float2 lo = x[t], old = bb_hi[t];
+                    bb[t] = make_float2(__fadd_rn(sg * lo.x, old.x), __fadd_rn(sg * lo.y, old.y));
+                }
                 __syncthreads();
-                if (tid == 0) ca.hi_diverged[slot] = 0;
+                for (int t = tid; t < h; t += TPB) {
+                    const float2 hi = x[h + t];
+                    bb_hi[t] = make_float2(sg * hi.x, sg * hi.y);
+                    const float2 b = bb[t];
+                    float o;
+                    if (mode == MODE_AM) {
+                        o = __fsqrt_rn(__fadd_rn(__fmul_rn(b.x, b.x), __fmul_rn(b.y, b.y)));  // dsp.cpp:116-126
+                    } else {
+                        const float2 pv = (t == 0) ? prev_last : bb[t - 1];
+                        const float c = pv.x, d = -pv.y;  // buf[i] * conj(prev), dsp.cpp:27-35
+                        const float re = __fsub_rn(__fmul_rn(b.x, c), __fmul_rn(b.y, d));
+                        const float im = __fadd_rn(__fmul_rn(b.x, d), __fmul_rn(b.y, c));
+                        o = atan2f(im, re);
+                    }
+                    nan_seen |= (o != o);
+                    audio[t] = o;
+                }
+                nan_seen = __syncthreads_or(nan_seen);
+                if (tid == 0) ca.bb_last[slot] = bb[h - 1];
+                if (!nan_seen && ca.hi_diverged[slot]) {
+                    // audio_real_prev <- audio_real[n/2..n) left behind by a NaN-dropped SSB frame
+                    for (int t = tid; t < h; t += TPB) real_prev[t] = real_hi[t];
+                    __syncthreads();
+                    if (tid == 0) ca.hi_diverged[slot] = 0;
+                }
             }
+            if (tid == 0) {
+                ca.valid_a[(size_t)f * ca.max_clients + slot] = nan_seen ? 0 : 1;
+                ca.pwr[(size_t)f * ca.max_clients + slot] = s_pw[fr];
+            }
+            __syncthreads();
         }
-        if (tid == 0) {
-            float tot = 0.f;
-#pragma unroll
-            for (int w = 0; w < TPB / 32; w++) tot += s_red[w];
-            ca.valid_a[(size_t)f * ca.max_clients + slot] = nan_seen ? 0 : 1;
-            ca.pwr[(size_t)f * ca.max_clients + slot] = tot;
-        }
-        __syncthreads();
     }
 }
 

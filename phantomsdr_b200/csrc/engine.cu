@@ -154,6 +154,7 @@ struct b200_engine {
     int tail_cpb = 32;
     size_t tail_smem = 0;
     int last_client_frames = 0;
+    int demod_fchunk = 1;
     long long *d_prof = nullptr;
 
     // pipelined host-block streaming (b200_stream_prime / b200_submit_block / b200_wait_block)
@@ -580,10 +581,10 @@ std::vector<int> factorize(int n) {
     return r;
 }
 
-constexpr int kDemodThreads = 128;
+constexpr int kDemodThreads = 256;
 
 int launch_demod(b200_engine *e, const ClientLaunch &cl) {
-    const size_t smem = sizeof(float2) * 2 * e->ca.n;
+    const size_t smem = sizeof(float2) * 2 * e->ca.n * e->demod_fchunk;
     if (cl.nactive == 0) {  // preparation call from clients_create
         CU(cudaFuncSetAttribute(client_demod_kernel<kDemodThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
@@ -681,6 +682,7 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     cl.order = e->d_order;
     cl.nactive = (int)e->order.size();
     cl.cpb = e->tail_cpb;
+    cl.fchunk = e->demod_fchunk;
     cl.prof = e->d_prof;
     int rc = launch_demod(e, cl);
     if (rc) return rc;
@@ -1072,7 +1074,20 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     std::vector<int> rad = factorize(audio_fft_size);
     if ((int)rad.size() > kMaxStages) return fail(B200_ENOTSUP, "audio_fft_size has too many factors");
     ca.nstages = (int)rad.size();
-    for (int i = 0; i < ca.nstages; i++) ca.radix[i] = rad[i];
+    {
+        auto magic = [](unsigned d) { return (unsigned)(((1ull << 32) / d) + 1); };  // x / d == umulhi(x, magic) for x*d < 2^32
+        unsigned sdiv = 1;
+        for (int i = 0; i < ca.nstages; i++) {
+            ca.radix[i] = rad[i];
+            ca.mul_s[i] = sdiv == 1 ? 0u : magic(sdiv);  // s = 1 handled below (umulhi(x, 2^32) does not fit)
+            ca.mul_items[i] = magic((unsigned)(audio_fft_size / rad[i]));
+            sdiv *= (unsigned)rad[i];
+        }
+        ca.mul_n = magic((unsigned)audio_fft_size);
+    }
+    // frames whose inverse FFTs are batched in shared memory by the demod kernel (2 buffers of fchunk * n complex)
+    e->demod_fchunk = std::max(1, std::min(e->batch, (int)((96 * 1024) / (sizeof(float2) * 2 * audio_fft_size))));
+    if (const char *v = getenv("B200_DEMOD_FCHUNK")) e->demod_fchunk = std::max(1, std::min(e->demod_fchunk, atoi(v)));
     {
         std::vector<float2> wn(audio_fft_size);
         for (int k = 0; k < audio_fft_size; k++) {
