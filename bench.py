@@ -58,8 +58,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-frames", type=int, default=256)
-    ap.add_argument("--mgpu-mode", default="spectrum", choices=["spectrum"],
-                    help="what crosses NVLink per frame (north_star: the spectrum frame)")
+    ap.add_argument("--mgpu-mode", default="spectrum", choices=["spectrum", "scatter"],
+                    help="N>1 exchange step. spectrum: NCCL broadcast of every spectrum batch (north_star). scatter: clients "
+                         "partitioned in (l, r) order and FFT pass 2 on the ingest rank stores each rank's sub-band straight "
+                         "into that rank's memory over NVLink (peer stores fused into the kernel, flags instead of a collective)")
     return ap.parse_args()
 
 
@@ -272,9 +274,14 @@ def workload_config(cfg, args, world):
         "frames_per_step": args.ring, "frames_per_launch": args.batch, "pipeline_banks": args.banks,
         "l2_policy": f"inputs larger than L2: {args.ring} hops x {cfg.hop_floats * 4 / 2**20:g} MiB resident ring, "
                      "each hop read by two consecutive frames only",
-        "parallelism": "single GPU" if world == 1 else
-                       f"rank 0 ingests + forward FFT; NCCL broadcast of each spectrum batch over NVLink; "
-                       f"{args.clients} clients demodulated per rank ({world} ranks)",
+        "parallelism": "single GPU" if world == 1 else (
+                       f"rank 0 ingests + forward FFT; clients of the whole job sorted by (l, r) and split into {world} "
+                       f"contiguous blocks; FFT pass 2 stores each rank's sub-band of every frame straight into that rank's "
+                       f"HBM over NVLink (peer stores inside the kernel, stream-ordered flags, no collective); "
+                       f"{args.clients} clients demodulated per rank" if (args.mgpu_mode == "scatter" and not cfg.is_real) else
+                       f"rank 0 ingests + forward FFT; NCCL broadcast of each spectrum batch over NVLink on a "
+                       f"communication stream (overlaps the next batch's FFT); "
+                       f"{args.clients} clients demodulated per rank ({world} ranks)"),
     }
 
 
@@ -304,7 +311,16 @@ def run_b200(args):
     eng.set_batch_frames(F)
     eng.set_pipeline(args.banks)
     eng.clients_create(args.clients, n, cfg.audio_sps)
-    for i, c in enumerate(client_table(cfg, args.clients, rank)):
+    scatter = world > 1 and args.mgpu_mode == "scatter" and not cfg.is_real
+    if scatter:
+        # the (l, r)-sorted client list of the WHOLE job, split into contiguous equal blocks
+        from phantomsdr_b200.parallel import partition_clients
+        everyone = client_table(cfg, args.clients * world, 0)
+        parts = partition_clients([(c.l, c.r) for c in everyone], world)
+        my_clients = [everyone[i] for i in parts[rank]]
+    else:
+        my_clients = client_table(cfg, args.clients, rank)
+    for i, c in enumerate(my_clients):
         eng.client_open(i, c.l, c.mid, c.r, c.mode)
     stream = torch.cuda.Stream(device=dev)  # a real (non-legacy) stream shared by torch/NCCL and the engine
     torch.cuda.set_stream(stream)
@@ -320,20 +336,83 @@ def run_b200(args):
         fill_ring(torch, ring_t, cfg, seed=0x5EED + 2)
     torch.cuda.synchronize()
 
+    # ---- scatter mode: IPC-mapped peer banks + flags ----
+    peer_ready, my_ready, r0_consumed, my_consumed = [], None, [], None
+    if scatter:
+        def sub_band(block):
+            """<= 2 half-open ranges of spectrum indices covering every slice of the block (src/websocket.cpp:182)."""
+            iv = sorted((cfg.slice_offset(c.l), cfg.slice_offset(c.l) + (c.r - c.l)) for c in block)
+            merged = []
+            for a, b in iv:
+                if merged and a <= merged[-1][1]:
+                    merged[-1][1] = max(merged[-1][1], b)
+                else:
+                    merged.append([a, b])
+            while len(merged) > 2:  # close the smallest gap (sending a few extra bins is harmless)
+                gi = min(range(len(merged) - 1), key=lambda i: merged[i + 1][0] - merged[i][1])
+                merged[gi][1] = merged[gi + 1][1]
+                del merged[gi + 1]
+            while len(merged) < 2:
+                merged.append([0, 0])
+            return merged
+
+        flags = eng.flag_buffer
+        mine = {"spec": eng.ipc_export(eng.spectrum_base), "flags": eng.ipc_export(flags)}
+        table = [None] * world
+        dist.all_gather_object(table, mine)
+        if rank == 0:
+            ptrs = []
+            for g in range(1, world):
+                ptrs.append(eng.ipc_open(table[g]["spec"]) + eng.spectrum_offset)
+                peer_ready.append(eng.ipc_open(table[g]["flags"]))          # flag 0 of rank g: "bank k has landed"
+                r0_consumed.append(flags + 8 * g)                           # flag g of rank 0: "rank g is done with bank k"
+            eng.set_peer_spectra(ptrs)
+            for g in range(1, world):
+                (a0, b0), (a1, b1) = sub_band([everyone[i] for i in parts[g]])
+                eng.set_peer_ranges(g - 1, a0, b0, a1, b1)
+        else:
+            my_ready = flags
+            my_consumed = eng.ipc_open(table[0]["flags"]) + 8 * rank
+        dist.barrier()
+
     frame_num = 0
     batch_no = 0
+    comm = torch.cuda.Stream(device=dev) if (world > 1 and not scatter) else None
+    ev_ready = [torch.cuda.Event() for _ in range(args.banks)]
+    ev_done = [torch.cuda.Event() for _ in range(args.banks)]
 
     def step():
         nonlocal frame_num, batch_no
         for g in range(H // F):
             bank = batch_no % args.banks
             eng.select_bank(bank)
+            if scatter:
+                seq = batch_no + 1
+                if rank == 0:
+                    if seq > args.banks:          # peers must have handed this bank back
+                        eng.enqueue_wait(False, r0_consumed, seq - args.banks)
+                    eng.execute_device(g * F, F)  # pass 2 also stores every rank's sub-band into that rank's bank
+                    eng.enqueue_signal(False, peer_ready, seq)
+                    eng.clients_execute_device(frame_num, F)
+                else:
+                    eng.enqueue_wait(True, [my_ready], seq)
+                    eng.clients_execute_device(frame_num, F)
+                    eng.enqueue_signal(True, [my_consumed], seq)
+                frame_num += F
+                batch_no += 1
+                continue
             if rank == 0:
-                eng.execute_device(g * F, F)
+                eng.execute_device(g * F, F)      # waits for this bank's previous clients, then FFT + pyramid
             else:
-                eng.bank_acquire()
+                eng.bank_acquire()                # the broadcast may overwrite the bank once its clients are done
             if world > 1:
-                dist.broadcast(spec_banks[bank], src=0)
+                # the exchange step runs on its own stream: broadcast k overlaps the forward FFT of batch k+1
+                ev_ready[bank].record(stream)
+                comm.wait_event(ev_ready[bank])
+                with torch.cuda.stream(comm):
+                    dist.broadcast(spec_banks[bank], src=0)
+                    ev_done[bank].record(comm)
+                eng.client_stream_wait_event(ev_done[bank].cuda_event)
             eng.clients_execute_device(frame_num, F)
             frame_num += F
             batch_no += 1
@@ -373,6 +452,11 @@ def run_b200(args):
     value = world * samples_per_step / (ms_step * 1e-3) / 1e6
     ingest = samples_per_step / (ms_step * 1e-3) / 1e6
 
+    if scatter:
+        barrier()
+        if rank == 0:
+            eng.set_peer_spectra([])  # the single-rank measurements below must not touch the peers
+        assert eng.flag_error == 0, "a flag wait timed out"
     # ---- roofline of the dominant kernel group (forward FFT + waterfall), timed alone on rank 0 ----
     roofline, breakdown = None, {}
     if rank == 0:

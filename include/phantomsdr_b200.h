@@ -162,6 +162,9 @@ int b200_set_pipeline(b200_engine *e, int banks);
 int b200_select_bank(b200_engine *e, int bank);
 int b200_bank_acquire(b200_engine *e);
 int b200_join_streams(b200_engine *e);
+/* Make the client stream wait for a caller-owned cudaEvent_t (e.g. the end of a collective that fills the selected
+ * bank on a communication stream) before the next b200_clients_execute_device. */
+int b200_client_stream_wait_event(b200_engine *e, void *cuda_event);
 /* Wait for everything enqueued on the engine's stream. */
 int b200_sync(b200_engine *e);
 /* The engine's cudaStream_t (as void*), so callers can order their own work / events on it. */
@@ -177,6 +180,20 @@ int b200_bind_spectrum(b200_engine *e, void *dev_ptr);
  * pointers valid on this device, e.g. from b200_ipc_open) from inside the last FFT pass, so the
  * NVLink transfer overlaps the butterflies. npeers = 0 turns it off. */
 int b200_set_peer_spectra(b200_engine *e, int npeers, void *const *dev_ptrs);
+/* Restrict what peer `peer` receives to the bins its clients read: two half-open ranges of spectrum indices
+ * (the IQ wrap tail is indices R .. R+additional). Default after b200_set_peer_spectra: everything. */
+int b200_set_peer_ranges(b200_engine *e, int peer, uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1);
+/* Base of the spectrum allocation (what CUDA IPC exports) and the byte offset of bank 0 / frame 0 / bin 0 in it. */
+void *b200_device_spectrum_base(b200_engine *e);
+size_t b200_device_spectrum_offset(b200_engine *e);
+/* 64 uint64 flags in device memory (zeroed; exportable with b200_ipc_export) and stream-ordered operations on
+ * flags that may live in this GPU's memory or in an IPC-mapped peer's: b200_enqueue_signal stores `value` after
+ * everything already enqueued on the chosen stream (0 = forward, 1 = client stream); b200_enqueue_wait holds the
+ * stream until every flag >= min_value (gives up after timeout_ms and latches b200_flag_error). */
+void *b200_flag_buffer(b200_engine *e);
+int b200_enqueue_signal(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t value);
+int b200_enqueue_wait(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t min_value, int timeout_ms);
+int b200_flag_error(b200_engine *e);
 /* CUDA IPC helpers for the above (64-byte handles). */
 int b200_ipc_export(b200_engine *e, const void *dev_ptr, uint8_t handle[64]);
 int b200_ipc_open(b200_engine *e, const uint8_t handle[64], void **dev_ptr);

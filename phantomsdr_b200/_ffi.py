@@ -47,11 +47,19 @@ SIGNATURES = {
     "b200_select_bank": (_i, [_vp, _i]),
     "b200_bank_acquire": (_i, [_vp]),
     "b200_join_streams": (_i, [_vp]),
+    "b200_client_stream_wait_event": (_i, [_vp, _vp]),
     "b200_sync": (_i, [_vp]),
     "b200_stream": (_vp, [_vp]),
     "b200_set_stream": (_i, [_vp, _vp]),
     "b200_bind_spectrum": (_i, [_vp, _vp]),
     "b200_set_peer_spectra": (_i, [_vp, _i, _pp]),
+    "b200_set_peer_ranges": (_i, [_vp, _i, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "b200_device_spectrum_base": (_vp, [_vp]),
+    "b200_device_spectrum_offset": (_sz, [_vp]),
+    "b200_flag_buffer": (_vp, [_vp]),
+    "b200_enqueue_signal": (_i, [_vp, _i, _pp, _i, _u64]),
+    "b200_enqueue_wait": (_i, [_vp, _i, _pp, _i, _u64, _i]),
+    "b200_flag_error": (_i, [_vp]),
     "b200_ipc_export": (_i, [_vp, _vp, _vp]),
     "b200_ipc_open": (_i, [_vp, _vp, _pp]),
     "b200_ipc_close": (_i, [_vp, _vp]),

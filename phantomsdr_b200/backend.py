@@ -151,6 +151,9 @@ class B200FFT:
     def join_streams(self) -> None:
         check(self.L.b200_join_streams(self.h))
 
+    def client_stream_wait_event(self, cuda_event: int) -> None:
+        check(self.L.b200_client_stream_wait_event(self.h, cuda_event))
+
     @property
     def hop_floats(self) -> int:
         return self.L.b200_hop_floats(self.h)
@@ -201,6 +204,33 @@ class B200FFT:
     def set_peer_spectra(self, ptrs: Sequence[int]) -> None:
         arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
         check(self.L.b200_set_peer_spectra(self.h, len(ptrs), arr))
+
+    def set_peer_ranges(self, peer: int, lo0: int, hi0: int, lo1: int = 0, hi1: int = 0) -> None:
+        check(self.L.b200_set_peer_ranges(self.h, peer, lo0, hi0, lo1, hi1))
+
+    @property
+    def spectrum_base(self) -> int:
+        return self.L.b200_device_spectrum_base(self.h)
+
+    @property
+    def spectrum_offset(self) -> int:
+        return self.L.b200_device_spectrum_offset(self.h)
+
+    @property
+    def flag_buffer(self) -> int:
+        return self.L.b200_flag_buffer(self.h)
+
+    def enqueue_signal(self, client_stream: bool, flag_ptrs: Sequence[int], value: int) -> None:
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        check(self.L.b200_enqueue_signal(self.h, int(client_stream), arr, len(flag_ptrs), value))
+
+    def enqueue_wait(self, client_stream: bool, flag_ptrs: Sequence[int], min_value: int, timeout_ms: int = 2000) -> None:
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        check(self.L.b200_enqueue_wait(self.h, int(client_stream), arr, len(flag_ptrs), min_value, timeout_ms))
+
+    @property
+    def flag_error(self) -> int:
+        return self.L.b200_flag_error(self.h)
 
     def ipc_export(self, dev_ptr: int) -> bytes:
         buf = (C.c_uint8 * 64)()

@@ -142,6 +142,9 @@ struct b200_engine {
 
     int npeers = 0;
     float2 *peers[kMaxPeers] = {};
+    unsigned peer_lo[kMaxPeers][2] = {}, peer_hi[kMaxPeers][2] = {};
+    unsigned long long *d_flags = nullptr;  // 64 stream-ordered flags (exportable over CUDA IPC)
+    int *d_flag_err = nullptr;
 
     // clients
     bool have_clients = false;
@@ -378,7 +381,14 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         p.scale = 1.0f / (float)e->size;
         p.additional = (int)e->additional;
         p.npeers = e->npeers;
-        for (int i = 0; i < e->npeers; i++) p.peers[i] = e->peers[i];
+        for (int i = 0; i < e->npeers; i++) {
+            // peer buffers are addressed like the local bank: same frame stride, same bank offset
+            p.peers[i] = e->peers[i] + (size_t)e->cur_bank * e->batch * e->spec_stride;
+            for (int j = 0; j < 2; j++) {
+                p.peer_lo[i][j] = e->peer_lo[i][j];
+                p.peer_hi[i][j] = e->peer_hi[i][j];
+            }
+        }
     } else {
         p.shift = 0;
         p.out = e->d_Z;
@@ -771,7 +781,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
+    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
@@ -988,6 +998,12 @@ int b200_bank_acquire(b200_engine *e) {
     CU(cudaSetDevice(e->device));
     return bank_acquire(e);
 }
+int b200_client_stream_wait_event(b200_engine *e, void *cuda_event) {
+    if (!e || !cuda_event) return fail(B200_EINVAL, "null argument");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamWaitEvent(e->client_stream(), reinterpret_cast<cudaEvent_t>(cuda_event), 0));
+    return 0;
+}
 int b200_join_streams(b200_engine *e) {
     if (!e) return fail(B200_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
@@ -1015,8 +1031,71 @@ int b200_set_peer_spectra(b200_engine *e, int npeers, void *const *dev_ptrs) {
     if (!e) return fail(B200_EINVAL, "null engine");
     if (npeers < 0 || npeers > kMaxPeers) return fail(B200_EINVAL, "npeers must be 0..%d", kMaxPeers);
     e->npeers = npeers;
-    for (int i = 0; i < npeers; i++) e->peers[i] = reinterpret_cast<float2 *>(dev_ptrs[i]);
+    for (int i = 0; i < npeers; i++) {
+        e->peers[i] = reinterpret_cast<float2 *>(dev_ptrs[i]);
+        e->peer_lo[i][0] = 0;  // default: the whole frame
+        e->peer_hi[i][0] = 0xffffffffu;
+        e->peer_lo[i][1] = e->peer_hi[i][1] = 0;
+    }
     return 0;
+}
+int b200_set_peer_ranges(b200_engine *e, int peer, uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (peer < 0 || peer >= e->npeers) return fail(B200_EINVAL, "peer %d out of range", peer);
+    e->peer_lo[peer][0] = lo0;
+    e->peer_hi[peer][0] = hi0;
+    e->peer_lo[peer][1] = lo1;
+    e->peer_hi[peer][1] = hi1;
+    return 0;
+}
+void *b200_device_spectrum_base(b200_engine *e) { return e ? e->d_spec_raw : nullptr; }
+size_t b200_device_spectrum_offset(b200_engine *e) { return e ? 15 * sizeof(float2) : 0; }
+void *b200_flag_buffer(b200_engine *e) {
+    if (!e) return nullptr;
+    if (!e->d_flags) {
+        cudaSetDevice(e->device);
+        if (cudaMalloc(&e->d_flags, 64 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+        cudaMemset(e->d_flags, 0, 64 * sizeof(unsigned long long));
+        if (cudaMalloc(&e->d_flag_err, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(e->d_flag_err, 0, sizeof(int));
+    }
+    return e->d_flags;
+}
+static int flag_list(b200_engine *e, void *const *flag_ptrs, int n, FlagList *fl) {
+    if (!e || !flag_ptrs) return fail(B200_EINVAL, "null argument");
+    if (n < 1 || n > kMaxPeers) return fail(B200_EINVAL, "1..%d flags per call", kMaxPeers);
+    if (!b200_flag_buffer(e)) return fail(B200_ENOMEM, "flag buffer allocation failed");
+    fl->n = n;
+    for (int i = 0; i < n; i++) fl->ptr[i] = reinterpret_cast<unsigned long long *>(flag_ptrs[i]);
+    return 0;
+}
+int b200_enqueue_signal(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t value) {
+    FlagList fl;
+    int rc = flag_list(e, flag_ptrs, n, &fl);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->device));
+    flag_signal_kernel<<<1, 32, 0, client_stream ? e->client_stream() : e->stream>>>(fl, value);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int b200_enqueue_wait(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t min_value, int timeout_ms) {
+    FlagList fl;
+    int rc = flag_list(e, flag_ptrs, n, &fl);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->device));
+    const long long cycles = (long long)timeout_ms * 1900000ll;  // ~1.9 GHz SM clock
+    flag_wait_kernel<<<1, 32, 0, client_stream ? e->client_stream() : e->stream>>>(fl, min_value, cycles, e->d_flag_err);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int b200_flag_error(b200_engine *e) {
+    if (!e || !e->d_flag_err) return 0;
+    int v = 0;
+    cudaSetDevice(e->device);
+    cudaMemcpy(&v, e->d_flag_err, sizeof(int), cudaMemcpyDeviceToHost);
+    return v;
 }
 int b200_ipc_export(b200_engine *e, const void *dev_ptr, uint8_t handle[64]) {
     if (!e || !dev_ptr || !handle) return fail(B200_EINVAL, "null argument");
@@ -1086,7 +1165,7 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
         ca.mul_n = magic((unsigned)audio_fft_size);
     }
     // frames whose inverse FFTs are batched in shared memory by the demod kernel (2 buffers of fchunk * n complex)
-    e->demod_fchunk = std::max(1, std::min(e->batch, (int)((96 * 1024) / (sizeof(float2) * 2 * audio_fft_size))));
+    e->demod_fchunk = std::max(1, std::min(std::min(e->batch, 4), (int)((96 * 1024) / (sizeof(float2) * 2 * audio_fft_size))));  // 4: measured optimum (occupancy vs lane use)
     if (const char *v = getenv("B200_DEMOD_FCHUNK")) e->demod_fchunk = std::max(1, std::min(e->demod_fchunk, atoi(v)));
     {
         std::vector<float2> wn(audio_fft_size);

@@ -47,6 +47,8 @@ struct FwdParams {
     const float2 *TH;        // W_M^(1024 j)
     int npeers;
     float2 *peers[kMaxPeers];  // extra spectrum destinations (NVLink peer memory)
+    // bins each peer needs (its clients' sub-band): up to two half-open ranges of spectrum indices, tail included
+    unsigned peer_lo[kMaxPeers][2], peer_hi[kMaxPeers][2];
     // fused waterfall epilogue of pass 2 (c2c): levels 0..log2(T)-1 straight from the FFT registers
     int8_t *quant;           // pyramid [frames][pyr_stride]
     size_t pyr_stride;
@@ -251,10 +253,14 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
                     float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
 #pragma unroll
                     for (int s = 0; s < RB; s++) {
-                        const size_t k = ((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1);
+                        const unsigned k = (unsigned)(((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1));
                         const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
-                        po[k] = val;
-                        if (k < (size_t)p.additional) po[M + k] = val;
+                        if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1]))
+                            po[k] = val;
+                        const unsigned kt = (unsigned)M + k;
+                        if (k < (unsigned)p.additional &&
+                            ((kt >= p.peer_lo[pe][0] && kt < p.peer_hi[pe][0]) || (kt >= p.peer_lo[pe][1] && kt < p.peer_hi[pe][1])))
+                            po[kt] = val;
                     }
                 }
             }
@@ -498,6 +504,37 @@ __global__ void pyramid_tail_kernel(const PyrParams p, int base_level, int level
             __syncthreads();
         }
         lvl_off += R >> lv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stream-ordered flags in (possibly peer) device memory: how the ingest rank tells the other ranks that a bank of
+// spectrum frames has landed in their memory, and how they hand the bank back, without the host in the loop.
+// ------------------------------------------------------------------------------------------------
+struct FlagList {
+    unsigned long long *ptr[kMaxPeers];
+    int n;
+};
+__global__ void flag_signal_kernel(FlagList fl, unsigned long long value) {
+    if (threadIdx.x < fl.n) {
+        __threadfence_system();  // everything earlier kernels of this stream wrote is visible before the flag
+        *reinterpret_cast<volatile unsigned long long *>(fl.ptr[threadIdx.x]) = value;
+        __threadfence_system();
+    }
+}
+// spins until every flag >= min_value; gives up after timeout_cycles (sets *err) so a lost peer cannot hang the GPU
+__global__ void flag_wait_kernel(FlagList fl, unsigned long long min_value, long long timeout_cycles, int *err) {
+    if (threadIdx.x < fl.n) {
+        const long long t0 = clock64();
+        volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(fl.ptr[threadIdx.x]);
+        while (*f < min_value) {
+            if (clock64() - t0 > timeout_cycles) {
+                *err = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        __threadfence_system();
     }
 }
 

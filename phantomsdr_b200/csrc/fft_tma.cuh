@@ -274,10 +274,14 @@ __global__ void __launch_bounds__(kTmaThreads, 2) fft_pass2_tma_kernel(const Fwd
                 float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
 #pragma unroll
                 for (int s = 0; s < RB; s++) {
-                    const size_t k = ((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1);
+                    const unsigned k = (unsigned)(((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1));
                     const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
-                    po[k] = val;
-                    if (k < (size_t)p.additional) po[M + k] = val;
+                    if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1]))
+                        po[k] = val;
+                    const unsigned kt = (unsigned)M + k;
+                    if (k < (unsigned)p.additional &&
+                        ((kt >= p.peer_lo[pe][0] && kt < p.peer_hi[pe][0]) || (kt >= p.peer_lo[pe][1] && kt < p.peer_hi[pe][1])))
+                        po[kt] = val;
                 }
             }
         }

@@ -1,0 +1,137 @@
+"""Worker of tests/test_gpu_multi.py (torchrun, NCCL, one rank per GPU): the spectrum exchange step.
+Every rank computes a LOCAL reference (its own forward FFT on the same input + its client block) and then the same
+client block on the spectrum delivered by the ingest rank, once by NCCL broadcast and once by the fused peer-store
+scatter of FFT pass 2 (CUDA IPC + stream-ordered flags). PCM must be bit-identical in all three."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+from phantomsdr_b200 import SpectrumConfig, USB, LSB, AM, FM  # noqa: E402
+from phantomsdr_b200.backend import B200FFT  # noqa: E402
+from phantomsdr_b200.parallel import partition_clients, SpectrumExchange  # noqa: E402
+from phantomsdr_b200.synth import SignalSource, make_clients  # noqa: E402
+
+
+def make(cfg, dev, F, nhops):
+    e = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, 0, dev)
+    e.set_output_additional_size(cfg.audio_fft_size)
+    e.plan_c2c()
+    e.set_hop_ring(nhops)
+    e.set_batch_frames(F)
+    e.set_pipeline(2)
+    return e
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cfg = SpectrumConfig(sps=35_000_000, fft_size=1 << 20)
+    n, h, F, nb = cfg.audio_fft_size, cfg.audio_fft_size // 2, 4, 3
+    nc = 24
+    everyone = make_clients(cfg, nc * world, seed=77, modes=(USB, LSB, AM, FM))
+    parts = partition_clients([(c.l, c.r) for c in everyone], world)
+    mine = [everyone[i] for i in parts[rank]]
+    src = SignalSource(cfg, seed=5, ntones=8)
+    hops = np.stack([src.next_hop().view(np.float32) for _ in range(F * nb + 1)])
+
+    def run(mode):
+        e = make(cfg, local, F, F * nb + 1)
+        e.clients_create(nc, n, cfg.audio_sps)
+        for i, c in enumerate(mine):
+            e.client_open(i, c.l, c.mid, c.r, c.mode)
+        stream = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(stream)
+        e.set_stream(stream.cuda_stream)
+        ring = torch.as_tensor(e.device_hop_ring(F * nb + 1), device=dev)
+        if mode == "local" or rank == 0:
+            ring.copy_(torch.from_numpy(hops))
+        banks = []
+        for b in range(2):
+            e.select_bank(b)
+            banks.append(torch.as_tensor(e.device_spectrum(F), device=dev))
+        peer_ready, r0_consumed, my_ready, my_consumed = [], [], None, None
+        if mode == "scatter":
+            flags = e.flag_buffer
+            table = [None] * world
+            dist.all_gather_object(table, {"spec": e.ipc_export(e.spectrum_base), "flags": e.ipc_export(flags)})
+            if rank == 0:
+                ptrs = []
+                for g in range(1, world):
+                    ptrs.append(e.ipc_open(table[g]["spec"]) + e.spectrum_offset)
+                    peer_ready.append(e.ipc_open(table[g]["flags"]))
+                    r0_consumed.append(flags + 8 * g)
+                e.set_peer_spectra(ptrs)
+                for g in range(1, world):
+                    blk = [everyone[i] for i in parts[g]]
+                    lo = min(cfg.slice_offset(c.l) for c in blk)
+                    iv = sorted((cfg.slice_offset(c.l), cfg.slice_offset(c.l) + c.r - c.l) for c in blk)
+                    # two ranges: below / above the wrap point of the display axis
+                    low = [x for x in iv if x[0] < cfg.fft_size // 2]
+                    high = [x for x in iv if x[0] >= cfg.fft_size // 2]
+                    r = [(min(a for a, _ in part), max(b for _, b in part)) if part else (0, 0) for part in (low, high)]
+                    e.set_peer_ranges(g - 1, r[0][0], r[0][1], r[1][0], r[1][1])
+            else:
+                my_ready = flags
+                my_consumed = e.ipc_open(table[0]["flags"]) + 8 * rank
+            dist.barrier()
+        ex = SpectrumExchange(world, rank)
+        out = []
+        for k in range(nb):
+            bank = k % 2
+            e.select_bank(bank)
+            seq = k + 1
+            if mode == "local":
+                e.execute_device(k * F, F)
+            elif mode == "broadcast":
+                if rank == 0:
+                    e.execute_device(k * F, F)
+                else:
+                    e.bank_acquire()
+                ex.broadcast(banks[bank])
+                assert ex.checksum_agrees(banks[bank])
+            else:
+                if rank == 0:
+                    if seq > 2:
+                        e.enqueue_wait(False, r0_consumed, seq - 2)
+                    e.execute_device(k * F, F)
+                    e.enqueue_signal(False, peer_ready, seq)
+                else:
+                    e.enqueue_wait(True, [my_ready], seq)
+            e.clients_execute_device(k * F, F)
+            if mode == "scatter" and rank != 0:
+                e.enqueue_signal(True, [my_consumed], seq)
+            for f in range(F):
+                pcm, pwr, valid = e.clients_fetch(f)
+                assert valid[:nc].all()
+                out.append(pcm.copy())
+        e.sync()
+        assert e.flag_error == 0
+        if mode == "scatter":
+            dist.barrier()
+        e.close()
+        return out
+
+    ref = run("local")
+    for mode in ("broadcast", "scatter"):
+        got = run(mode)
+        for f, (a, b) in enumerate(zip(ref, got)):
+            assert np.array_equal(a, b), f"rank {rank} mode {mode} frame {f}: PCM differs"
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_EXCHANGE_OK")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
