@@ -118,6 +118,7 @@ int b200_execute(b200_engine *e);
                                    pyramid kernel.) Measured at 2^20, 16 frames/launch: 10.1 / 10.9 / 12.1 us per frame. */
 #define B200_OPT_TMA 6           /* 1 (default): persistent TMA-fed FFT passes where available (2^20-point transforms) */
 #define B200_OPT_TAIL_PIPELINE 7 /* 1 (default): frame-skewed software pipeline for the DC/AGC tails when >= 4 frames per call */
+#define B200_OPT_PEER_STORES 8   /* 1 (default): FFT pass 2 stores the peers' sub-bands itself; 0: leave it to b200_push_peers */
 #define B200_OPT_STAGE_MASK 4    /* profiling aid: bit0 = FFT pass 1, bit1 = pass 2, bit2 = pyramid; default 7 */
 int b200_set_option(b200_engine *e, int option, int value);
 
@@ -188,8 +189,12 @@ void *b200_device_spectrum_base(b200_engine *e);
 size_t b200_device_spectrum_offset(b200_engine *e);
 /* 64 uint64 flags in device memory (zeroed; exportable with b200_ipc_export) and stream-ordered operations on
  * flags that may live in this GPU's memory or in an IPC-mapped peer's: b200_enqueue_signal stores `value` after
- * everything already enqueued on the chosen stream (0 = forward, 1 = client stream); b200_enqueue_wait holds the
+ * everything already enqueued on the chosen stream (0 = forward, 1 = client, 2 = copy stream); b200_enqueue_wait holds the
  * stream until every flag >= min_value (gives up after timeout_ms and latches b200_flag_error). */
+/* Copy-engine form of the scatter: after the forward work already enqueued, DMA every peer's sub-band of the
+ * selected bank (`nframes` frames) into that peer's bank on the engine's copy stream (selector 2 of the flag
+ * calls). Use with b200_set_option(B200_OPT_PEER_STORES, 0). */
+int b200_push_peers(b200_engine *e, int nframes);
 void *b200_flag_buffer(b200_engine *e);
 int b200_enqueue_signal(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t value);
 int b200_enqueue_wait(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t min_value, int timeout_ms);

@@ -20,7 +20,7 @@ from ._ffi import B200Error, check  # noqa: F401
 
 FORWARD, BACKWARD = 0, 1
 FMT_F32, FMT_U8, FMT_S8, FMT_U16, FMT_S16 = 0, 1, 2, 3, 4
-OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_TAIL_PIPELINE = 1, 2, 3, 4, 5, 6, 7
+OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_TAIL_PIPELINE, OPT_PEER_STORES = 1, 2, 3, 4, 5, 6, 7, 8
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 
@@ -208,6 +208,9 @@ class B200FFT:
     def set_peer_ranges(self, peer: int, lo0: int, hi0: int, lo1: int = 0, hi1: int = 0) -> None:
         check(self.L.b200_set_peer_ranges(self.h, peer, lo0, hi0, lo1, hi1))
 
+    def push_peers(self, nframes: int) -> None:
+        check(self.L.b200_push_peers(self.h, nframes))
+
     @property
     def spectrum_base(self) -> int:
         return self.L.b200_device_spectrum_base(self.h)
@@ -220,11 +223,12 @@ class B200FFT:
     def flag_buffer(self) -> int:
         return self.L.b200_flag_buffer(self.h)
 
-    def enqueue_signal(self, client_stream: bool, flag_ptrs: Sequence[int], value: int) -> None:
+    # stream selectors of the flag calls: 0 forward, 1 client, 2 copy stream
+    def enqueue_signal(self, client_stream, flag_ptrs: Sequence[int], value: int) -> None:
         arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
         check(self.L.b200_enqueue_signal(self.h, int(client_stream), arr, len(flag_ptrs), value))
 
-    def enqueue_wait(self, client_stream: bool, flag_ptrs: Sequence[int], min_value: int, timeout_ms: int = 2000) -> None:
+    def enqueue_wait(self, client_stream, flag_ptrs: Sequence[int], min_value: int, timeout_ms: int = 2000) -> None:
         arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
         check(self.L.b200_enqueue_wait(self.h, int(client_stream), arr, len(flag_ptrs), min_value, timeout_ms))
 

@@ -144,6 +144,9 @@ struct b200_engine {
     float2 *peers[kMaxPeers] = {};
     unsigned peer_lo[kMaxPeers][2] = {}, peer_hi[kMaxPeers][2] = {};
     unsigned long long *d_flags = nullptr;  // 64 stream-ordered flags (exportable over CUDA IPC)
+    int opt_peer_stores = 1;                // 1: FFT pass 2 stores into the peers itself; 0: b200_push_peers (copy engines)
+    cudaEvent_t ev_push[4] = {}, ev_fwd_done = nullptr;
+    bool push_pending[4] = {};
     int *d_flag_err = nullptr;
 
     // clients
@@ -349,6 +352,10 @@ int bank_acquire(b200_engine *e) {
         CU(cudaStreamWaitEvent(e->stream, e->ev_cli[e->cur_bank], 0));
         e->cli_pending[e->cur_bank] = false;
     }
+    if (e->push_pending[e->cur_bank]) {  // a copy-engine push to the peers may still be reading the bank
+        CU(cudaStreamWaitEvent(e->stream, e->ev_push[e->cur_bank], 0));
+        e->push_pending[e->cur_bank] = false;
+    }
     return 0;
 }
 
@@ -380,8 +387,8 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         p.out_stride = e->spec_stride;
         p.scale = 1.0f / (float)e->size;
         p.additional = (int)e->additional;
-        p.npeers = e->npeers;
-        for (int i = 0; i < e->npeers; i++) {
+        p.npeers = e->opt_peer_stores ? e->npeers : 0;
+        for (int i = 0; i < p.npeers; i++) {
             // peer buffers are addressed like the local bank: same frame stride, same bank offset
             p.peers[i] = e->peers[i] + (size_t)e->cur_bank * e->batch * e->spec_stride;
             for (int j = 0; j < 2; j++) {
@@ -893,6 +900,7 @@ int b200_set_option(b200_engine *e, int option, int value) {
         e->opt_fused_pyramid = value;
         return 0;
     case B200_OPT_TMA: e->opt_tma = value ? 1 : 0; return 0;
+    case B200_OPT_PEER_STORES: e->opt_peer_stores = value ? 1 : 0; return 0;
     case B200_OPT_TAIL_PIPELINE: e->opt_tail_pipe = value ? 1 : 0; return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
@@ -1061,6 +1069,46 @@ void *b200_flag_buffer(b200_engine *e) {
     }
     return e->d_flags;
 }
+static int stream_setup(b200_engine *e);
+static int pick_stream(b200_engine *e, int which, cudaStream_t *out) {
+    if (which == 2) {
+        int rc = stream_setup(e);
+        if (rc) return rc;
+        *out = e->copy_stream;
+    } else {
+        *out = which ? e->client_stream() : e->stream;
+    }
+    return 0;
+}
+int b200_push_peers(b200_engine *e, int nframes) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (nframes < 1 || nframes > e->batch) return fail(B200_EINVAL, "nframes %d outside 1..%d", nframes, e->batch);
+    CU(cudaSetDevice(e->device));
+    int rc = stream_setup(e);
+    if (rc) return rc;
+    if (!e->ev_fwd_done) {
+        CU(cudaEventCreateWithFlags(&e->ev_fwd_done, cudaEventDisableTiming));
+        for (int b = 0; b < 4; b++) CU(cudaEventCreateWithFlags(&e->ev_push[b], cudaEventDisableTiming));
+    }
+    // the selected bank as the forward stream leaves it -> every peer's sub-band, by the copy engines
+    CU(cudaEventRecord(e->ev_fwd_done, e->stream));
+    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_fwd_done, 0));
+    const size_t bank_off = (size_t)e->cur_bank * e->batch * e->spec_stride;
+    const float2 *src = e->d_spec + bank_off;
+    const size_t pitch = e->spec_stride * sizeof(float2);
+    for (int i = 0; i < e->npeers; i++) {
+        float2 *dst = e->peers[i] + bank_off;
+        for (int j = 0; j < 2; j++) {
+            size_t lo = e->peer_lo[i][j], hi = std::min<size_t>(e->peer_hi[i][j], e->spec_stride);
+            if (hi <= lo) continue;
+            CU(cudaMemcpy2DAsync(dst + lo, pitch, src + lo, pitch, (hi - lo) * sizeof(float2), nframes, cudaMemcpyDeviceToDevice,
+                                 e->copy_stream));
+        }
+    }
+    CU(cudaEventRecord(e->ev_push[e->cur_bank], e->copy_stream));
+    e->push_pending[e->cur_bank] = true;
+    return 0;
+}
 static int flag_list(b200_engine *e, void *const *flag_ptrs, int n, FlagList *fl) {
     if (!e || !flag_ptrs) return fail(B200_EINVAL, "null argument");
     if (n < 1 || n > kMaxPeers) return fail(B200_EINVAL, "1..%d flags per call", kMaxPeers);
@@ -1074,7 +1122,10 @@ int b200_enqueue_signal(b200_engine *e, int client_stream, void *const *flag_ptr
     int rc = flag_list(e, flag_ptrs, n, &fl);
     if (rc) return rc;
     CU(cudaSetDevice(e->device));
-    flag_signal_kernel<<<1, 32, 0, client_stream ? e->client_stream() : e->stream>>>(fl, value);
+    cudaStream_t st;
+    rc = pick_stream(e, client_stream, &st);
+    if (rc) return rc;
+    flag_signal_kernel<<<1, 32, 0, st>>>(fl, value);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -1085,7 +1136,10 @@ int b200_enqueue_wait(b200_engine *e, int client_stream, void *const *flag_ptrs,
     if (rc) return rc;
     CU(cudaSetDevice(e->device));
     const long long cycles = (long long)timeout_ms * 1900000ll;  // ~1.9 GHz SM clock
-    flag_wait_kernel<<<1, 32, 0, client_stream ? e->client_stream() : e->stream>>>(fl, min_value, cycles, e->d_flag_err);
+    cudaStream_t st;
+    rc = pick_stream(e, client_stream, &st);
+    if (rc) return rc;
+    flag_wait_kernel<<<1, 32, 0, st>>>(fl, min_value, cycles, e->d_flag_err);
     e->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -15,7 +15,7 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 from phantomsdr_b200 import SpectrumConfig, USB, LSB, AM, FM  # noqa: E402
-from phantomsdr_b200.backend import B200FFT  # noqa: E402
+from phantomsdr_b200.backend import B200FFT, OPT_PEER_STORES  # noqa: E402
 from phantomsdr_b200.parallel import partition_clients, SpectrumExchange  # noqa: E402
 from phantomsdr_b200.synth import SignalSource, make_clients  # noqa: E402
 
@@ -61,7 +61,7 @@ def main():
             e.select_bank(b)
             banks.append(torch.as_tensor(e.device_spectrum(F), device=dev))
         peer_ready, r0_consumed, my_ready, my_consumed = [], [], None, None
-        if mode == "scatter":
+        if mode in ("scatter", "scatter-dma"):
             flags = e.flag_buffer
             table = [None] * world
             dist.all_gather_object(table, {"spec": e.ipc_export(e.spectrum_base), "flags": e.ipc_export(flags)})
@@ -81,6 +81,8 @@ def main():
                     high = [x for x in iv if x[0] >= cfg.fft_size // 2]
                     r = [(min(a for a, _ in part), max(b for _, b in part)) if part else (0, 0) for part in (low, high)]
                     e.set_peer_ranges(g - 1, r[0][0], r[0][1], r[1][0], r[1][1])
+                if mode == "scatter-dma":
+                    e.set_option(OPT_PEER_STORES, 0)
             else:
                 my_ready = flags
                 my_consumed = e.ipc_open(table[0]["flags"]) + 8 * rank
@@ -100,6 +102,12 @@ def main():
                     e.bank_acquire()
                 ex.broadcast(banks[bank])
                 assert ex.checksum_agrees(banks[bank])
+            elif mode == "scatter-dma" and rank == 0:
+                e.execute_device(k * F, F)
+                if seq > 2:
+                    e.enqueue_wait(2, r0_consumed, seq - 2)
+                e.push_peers(F)
+                e.enqueue_signal(2, peer_ready, seq)
             else:
                 if rank == 0:
                     if seq > 2:
@@ -109,7 +117,7 @@ def main():
                 else:
                     e.enqueue_wait(True, [my_ready], seq)
             e.clients_execute_device(k * F, F)
-            if mode == "scatter" and rank != 0:
+            if mode != "local" and mode != "broadcast" and rank != 0:
                 e.enqueue_signal(True, [my_consumed], seq)
             for f in range(F):
                 pcm, pwr, valid = e.clients_fetch(f)
@@ -117,13 +125,13 @@ def main():
                 out.append(pcm.copy())
         e.sync()
         assert e.flag_error == 0
-        if mode == "scatter":
+        if mode in ("scatter", "scatter-dma"):
             dist.barrier()
         e.close()
         return out
 
     ref = run("local")
-    for mode in ("broadcast", "scatter"):
+    for mode in ("broadcast", "scatter", "scatter-dma"):
         got = run(mode)
         for f, (a, b) in enumerate(zip(ref, got)):
             assert np.array_equal(a, b), f"rank {rank} mode {mode} frame {f}: PCM differs"
