@@ -133,9 +133,15 @@ struct b200_engine {
     int opt_reload_both = 0;
     int opt_mirror = 3;
     int opt_stage_mask = 7;
-    int opt_fused_pyramid = 2;
-    int opt_tma = 1;
+    int opt_fused_pyramid = -1;         // -1 auto: 0 with the TMA passes (2^20), 2 with the generic passes
+    int opt_tma = 2;
     int opt_tail_pipe = 1;
+    int opt_packed = 1;                 // bit0: packed-f32 (FMUL2/FADD2) waterfall quantiser
+    int opt_pass1_order = 0;            // item order of the TMA pass 1 (see fft_pass1_tma_kernel)
+    int opt_lanes = 1;                  // forward lanes: sub-batches of a batch run on this many streams
+    int opt_sub_frames = 64;            // frames per sub-batch (>= batch: one launch group per batch)
+    cudaStream_t lane_stream[4] = {};
+    cudaEvent_t ev_fork = nullptr, ev_lane[4] = {};
     bool tma_ok = false;
     int num_sms = 148;
     CUtensorMap ring_map{}, window_map{};
@@ -313,6 +319,10 @@ int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
     CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
     CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
     CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
+    CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     e->tma_ok = true;
     return 0;
 }
@@ -323,20 +333,33 @@ int tma_ring_map(b200_engine *e) {  // whenever the hop ring is (re)allocated
 }
 
 int launch_tma_pass1(b200_engine *e, const FwdParams &p, int frames) {
-    const int nsplit = frames >= 2 ? 2 : 1;  // two CTAs share a column tile (even / odd frames): one wave on 2 CTAs per SM
-    const int grid = (kS / kTmaT) * nsplit;
+    // order 0: two CTAs share a column tile (even / odd frames); 1 / 2: equal chunks of the tile- / frame-major item list
+    const int order = e->opt_pass1_order;
+    const int nsplit = frames >= 2 ? 2 : 1;
+    const int grid = order == 0 ? (kS / kTmaT) * nsplit : std::min((kS / kTmaT) * frames, 2 * e->num_sms);
     if (e->is_real)
         fft_pass1_tma_kernel<true><<<grid, kTmaThreads, TmaSmem::kPass1R, e->stream>>>(p, e->ring_map, e->window_map, frames,
-                                                                                       nsplit);
+                                                                                       order, nsplit);
     else
         fft_pass1_tma_kernel<false><<<grid, kTmaThreads, TmaSmem::kPass1C, e->stream>>>(p, e->ring_map, e->window_map, frames,
-                                                                                        nsplit);
+                                                                                        order, nsplit);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse) {
     const int total = (kS / kTmaT) * frames;
+    if (e->opt_tma >= 2 && fuse != 1) {  // three-stage variant: one CTA of two consumer groups per SM
+        const int grid = std::min(total, e->num_sms);
+        const bool peers = p.npeers > 0;
+        if (fuse == 2 && !peers) fft_pass2_tma3_kernel<2, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
+        else if (fuse == 2) fft_pass2_tma3_kernel<2, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
+        else if (!peers) fft_pass2_tma3_kernel<0, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
+        else fft_pass2_tma3_kernel<0, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
+        e->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     const int grid = std::min(total, 2 * e->num_sms);
     if (fuse == 1) fft_pass2_tma_kernel<1><<<grid, kTmaThreads, TmaSmem::kPass2, e->stream>>>(p, frames);
     else if (fuse == 2) fft_pass2_tma_kernel<2><<<grid, kTmaThreads, TmaSmem::kPass2, e->stream>>>(p, frames);
@@ -359,19 +382,17 @@ int bank_acquire(b200_engine *e) {
     return 0;
 }
 
-int run_forward(b200_engine *e, long hop0, int frames) {
-    {
-        int rc0 = bank_acquire(e);
-        if (rc0) return rc0;
-    }
+// frames [f0, f0 + frames) of the batch that starts at ring hop `hop0`, scratch slots of `lane`, on e->stream
+int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
+    const size_t slot0 = (size_t)lane * e->opt_sub_frames;  // first scratch frame slot of this lane
     FwdParams p{};
     p.ring = e->d_ring;
     p.hop_bytes = e->hop_samples * e->format_bytes();
     p.nhops = (int)e->nhops;
-    p.hop0 = (int)hop0;
+    p.hop0 = (int)((hop0 + f0) % (long)e->nhops);
     p.in_format = e->in_format;
     p.window = e->d_window;
-    p.Y = e->d_Y;
+    p.Y = e->d_Y + slot0 * e->M;
     p.log2M = e->log2M;
     p.N1 = e->sp1.S;
     p.N2 = e->sp2.S;
@@ -380,7 +401,7 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     p.twA2 = e->d_twA2;
     p.TL = e->d_TL;
     p.TH = e->d_TH;
-    float2 *spec = e->spec_ptr();
+    float2 *spec = e->spec_ptr() + (size_t)f0 * e->spec_stride;
     if (!e->is_real) {
         p.shift = 1;
         p.out = spec;
@@ -390,7 +411,7 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         p.npeers = e->opt_peer_stores ? e->npeers : 0;
         for (int i = 0; i < p.npeers; i++) {
             // peer buffers are addressed like the local bank: same frame stride, same bank offset
-            p.peers[i] = e->peers[i] + (size_t)e->cur_bank * e->batch * e->spec_stride;
+            p.peers[i] = e->peers[i] + ((size_t)e->cur_bank * e->batch + f0) * e->spec_stride;
             for (int j = 0; j < 2; j++) {
                 p.peer_lo[i][j] = e->peer_lo[i][j];
                 p.peer_hi[i][j] = e->peer_hi[i][j];
@@ -398,18 +419,21 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         }
     } else {
         p.shift = 0;
-        p.out = e->d_Z;
+        p.out = e->d_Z + slot0 * e->M;
         p.out_stride = e->M;
         p.scale = 1.0f;
         p.additional = 0;
         p.npeers = 0;
     }
-    const int fuse = e->is_real ? 0 : e->opt_fused_pyramid;  // 0 none, 1 full epilogue in pass 2, 2 |X|^2 from pass 2
+    // 0 none (pyramid kernel re-reads the spectrum), 1 full epilogue in pass 2, 2 |X|^2 plane from pass 2
+    const int fuse = e->is_real ? 0 : (e->opt_fused_pyramid >= 0 ? e->opt_fused_pyramid : (tma_path(e) ? 0 : 2));
     int base_level = 0;
     while ((1 << base_level) < e->sp2.T) base_level++;
-    p.quant = e->quant_ptr();
+    int8_t *quant = e->quant_ptr() + (size_t)f0 * e->pyr_stride;
+    float *pscratch = e->d_pscratch + slot0 * e->M;
+    p.quant = quant;
     p.pyr_stride = e->pyr_stride;
-    p.pscratch = e->d_pscratch;
+    p.pscratch = pscratch;
     p.levels = e->levels;
     p.size_log2 = e->size_log2;
     int rc = 0;
@@ -427,10 +451,10 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     PyrParams q{};
     q.spec = spec;
     q.spec_stride = e->spec_stride;
-    q.Z = e->d_Z;
-    q.quant = e->quant_ptr();
+    q.Z = e->d_Z + slot0 * e->M;
+    q.quant = quant;
     q.pyr_stride = e->pyr_stride;
-    q.ptop = e->d_ptop;
+    q.ptop = e->d_ptop + slot0 * std::max<size_t>(1, e->R / 1024);
     int log2R = 0;
     while (((size_t)1 << log2R) < e->R) log2R++;
     q.log2R = log2R;
@@ -439,20 +463,30 @@ int run_forward(b200_engine *e, long hop0, int frames) {
     q.scale = 1.0f / (float)e->size;
     q.TLr = e->d_TLr;
     q.THr = e->d_THr;
-    q.pscratch = e->d_pscratch;
+    q.pscratch = pscratch;
     q.base_level = fuse == 1 ? base_level : 0;
     q.ntiles = fuse == 2 ? e->sp1.S : (tma ? kS / kTmaT : e->sp1.S / e->sp2.T);
     q.N2 = e->sp2.S;
     q.npeers = e->is_real ? e->npeers : 0;
-    for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i];
+    for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i] + (size_t)f0 * e->spec_stride;
     if (e->levels > q.base_level) {
         // 16 entries per thread for the full-resolution inputs, 4 for the small per-tile sums of mode 1
         const int per = (fuse == 1) ? 4 : 16;
         dim3 grid((unsigned)((e->R >> q.base_level) / (256 * per)), frames);
-        if (e->is_real) pyramid_kernel<PYR_R2C, 16><<<grid, 256, 0, e->stream>>>(q);
-        else if (fuse == 1) pyramid_kernel<PYR_SCRATCH, 4><<<grid, 256, 0, e->stream>>>(q);
-        else if (fuse == 2) pyramid_kernel<PYR_POWER, 16><<<grid, 256, 0, e->stream>>>(q);
-        else pyramid_kernel<PYR_SPEC, 16><<<grid, 256, 0, e->stream>>>(q);
+        const bool pk = e->opt_packed & 1;
+        if (e->is_real) {
+            if (pk) pyramid_kernel<PYR_R2C, 16, true><<<grid, 256, 0, e->stream>>>(q);
+            else pyramid_kernel<PYR_R2C, 16, false><<<grid, 256, 0, e->stream>>>(q);
+        } else if (fuse == 1) {
+            if (pk) pyramid_kernel<PYR_SCRATCH, 4, true><<<grid, 256, 0, e->stream>>>(q);
+            else pyramid_kernel<PYR_SCRATCH, 4, false><<<grid, 256, 0, e->stream>>>(q);
+        } else if (fuse == 2) {
+            if (pk) pyramid_kernel<PYR_POWER, 16, true><<<grid, 256, 0, e->stream>>>(q);
+            else pyramid_kernel<PYR_POWER, 16, false><<<grid, 256, 0, e->stream>>>(q);
+        } else {
+            if (pk) pyramid_kernel<PYR_SPEC, 16, true><<<grid, 256, 0, e->stream>>>(q);
+            else pyramid_kernel<PYR_SPEC, 16, false><<<grid, 256, 0, e->stream>>>(q);
+        }
         e->launches++;
         CU(cudaGetLastError());
         const int levels_done = (per == 16 ? 4 : 2) + 9;
@@ -463,6 +497,52 @@ int run_forward(b200_engine *e, long hop0, int frames) {
         }
     }
     return 0;
+}
+
+// forward FFT + pyramid for `frames` consecutive frames starting at ring hop `hop0`. With lanes > 1 the batch is cut
+// into sub-batches of opt_sub_frames frames that alternate over the lane streams: every sub-batch's intermediates
+// (Y, |X|^2) live in its lane's small scratch slots, which are rewritten while still resident in L2 (no DRAM round
+// trip), and the lanes fill each other's launch gaps and partial waves.
+int run_forward(b200_engine *e, long hop0, int frames) {
+    {
+        int rc0 = bank_acquire(e);
+        if (rc0) return rc0;
+    }
+    int sub = std::max(1, std::min(e->opt_sub_frames, e->batch));
+    int lanes = std::max(1, std::min({e->opt_lanes, 4, e->batch / sub}));
+    if (sub >= frames) lanes = 1;
+    if (lanes == 1 && sub >= frames) return forward_range(e, hop0, 0, frames, 0);
+    if (lanes == 1) {  // sub-batches back to back on the one stream (scratch slot 0 reused)
+        for (int f0 = 0; f0 < frames; f0 += sub) {
+            int rc = forward_range(e, hop0, f0, std::min(sub, frames - f0), 0);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    for (int l = 0; l < lanes; l++)
+        if (!e->lane_stream[l]) {
+            CU(cudaStreamCreateWithFlags(&e->lane_stream[l], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&e->ev_lane[l], cudaEventDisableTiming));
+        }
+    if (!e->ev_fork) CU(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(e->ev_fork, e->stream));
+    cudaStream_t main_stream = e->stream;
+    int rc = 0, used = 0;
+    for (int f0 = 0, i = 0; f0 < frames && !rc; f0 += sub, i++) {
+        const int l = i % lanes;
+        if (i < lanes) {
+            CU(cudaStreamWaitEvent(e->lane_stream[l], e->ev_fork, 0));
+            used = i + 1;
+        }
+        e->stream = e->lane_stream[l];
+        rc = forward_range(e, hop0, f0, std::min(sub, frames - f0), l);
+        e->stream = main_stream;
+    }
+    for (int l = 0; l < used; l++) {
+        CU(cudaEventRecord(e->ev_lane[l], e->lane_stream[l]));
+        CU(cudaStreamWaitEvent(main_stream, e->ev_lane[l], 0));
+    }
+    return rc;
 }
 
 int plan_common(b200_engine *e, bool is_real) {
@@ -896,12 +976,25 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_HOST_MIRROR: e->opt_mirror = value & 3; return 0;
     case B200_OPT_STAGE_MASK: e->opt_stage_mask = value & 7; return 0;
     case B200_OPT_FUSED_PYRAMID:
-        if (value < 0 || value > 2) return fail(B200_EINVAL, "fused pyramid mode must be 0, 1 or 2");
+        if (value < -1 || value > 2) return fail(B200_EINVAL, "fused pyramid mode must be -1 (auto), 0, 1 or 2");
         e->opt_fused_pyramid = value;
         return 0;
-    case B200_OPT_TMA: e->opt_tma = value ? 1 : 0; return 0;
+    case B200_OPT_TMA: e->opt_tma = value < 0 ? 0 : (value > 3 ? 3 : value); return 0;
     case B200_OPT_PEER_STORES: e->opt_peer_stores = value ? 1 : 0; return 0;
     case B200_OPT_TAIL_PIPELINE: e->opt_tail_pipe = value ? 1 : 0; return 0;
+    case B200_OPT_PACKED_MATH: e->opt_packed = value & 1; return 0;
+    case B200_OPT_PASS1_ORDER:
+        if (value < 0 || value > 2) return fail(B200_EINVAL, "pass-1 order must be 0, 1 or 2");
+        e->opt_pass1_order = value;
+        return 0;
+    case B200_OPT_FWD_LANES:
+        if (value < 1 || value > 4) return fail(B200_EINVAL, "forward lanes must be 1..4");
+        e->opt_lanes = value;
+        return 0;
+    case B200_OPT_FWD_SUB_FRAMES:
+        if (value < 1 || value > 64) return fail(B200_EINVAL, "sub-batch frames must be 1..64");
+        e->opt_sub_frames = value;
+        return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
         if (value != e->in_format) {

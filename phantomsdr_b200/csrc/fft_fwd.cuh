@@ -153,20 +153,95 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
 // waterfall quantiser - bit-exact restatement of vec_log2 / power_and_quantize (src/fft_impl.cpp:14-44).
 // Every float op is an explicit round-to-nearest intrinsic (no FMA contraction) in source order.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float vec_log2_dev(float val, int power_offset) {
-    unsigned bits = __float_as_uint(val);
-    float log_val = __fadd_rn((float)((int)((bits >> 23) & 0xFF) - 128), (float)power_offset);
-    bits &= ~(255u << 23);
-    bits += 127u << 23;
-    val = __uint_as_float(bits);
+// The exponent reaches the float domain without an I2F (the conversion pipe is quarter-rate): 0x4B000000 | e is the
+// float 2^23 + e, and (2^23 + e) - (2^23 + 128 - offset) is exact, so log_val has the bits of
+// (float)(e - 128) + (float)offset (fft_impl.cpp:16-17) for every e and every offset in range.
+__device__ __forceinline__ float quant_bias(int power_offset) { return (float)(8388608 + 128 - power_offset); }
+// (a & b) | c in one LOP3 with both masks in registers (as immediates ptxas needs two instructions)
+__device__ __forceinline__ unsigned and_or(unsigned a, unsigned b, unsigned c) {
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ float exponent_as_float(unsigned bits) { return __uint_as_float(and_or(bits >> 23, 0xFFu, 0x4B000000u)); }
+__device__ __forceinline__ float mantissa_1_2(unsigned bits) { return __uint_as_float(and_or(bits, 0x007FFFFFu, 0x3F800000u)); }
+__device__ __forceinline__ float vec_log2_biased(float val, float bias) {
+    const unsigned bits = __float_as_uint(val);
+    const float log_val = __fsub_rn(exponent_as_float(bits), bias);
+    val = mantissa_1_2(bits);  // mantissa forced to [1, 2)
     float poly = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(-0.34484843f, val), 2.02466578f), val), 0.67487759f);
     return __fadd_rn(log_val, poly);
 }
+__device__ __forceinline__ float vec_log2_dev(float val, int power_offset) { return vec_log2_biased(val, quant_bias(power_offset)); }
+__device__ __forceinline__ int quantize_biased(float power, float bias) {
+    float v = __fadd_rn(__fmul_rn(__fmul_rn(vec_log2_biased(power, bias), 0.3010299956639812f), 20.f), 127.f);
+    v = fmaxf(v, -128.f);                 // std::max(-128.f, v); NaN -> -128
+    return __float2int_rz(v);             // C truncation; the int8 store keeps the low byte (wraps above 127 like x86)
+}
 __device__ __forceinline__ int quantize_dev(float power, int power_offset) {
-    float v = __fadd_rn(__fmul_rn(__fmul_rn(vec_log2_dev(power, power_offset), 0.3010299956639812f), 20.f), 127.f);
-    v = (v > -128.f) ? v : -128.f;        // std::max(-128.f, v); NaN -> -128
-    int t = __float2int_rz(v);            // C truncation
-    return t & 0xFF;                      // int8 store keeps the low byte (wraps above 127 like x86)
+    return quantize_biased(power, quant_bias(power_offset)) & 0xFF;
+}
+// Two bins per instruction on the sm_100 packed-f32 pipe where that keeps the reference's rounding: ptxas contracts
+// every mul.f32x2 -> add.f32x2 chain into FFMA2 (one rounding instead of two, even with explicit .rn and
+// -fmad=false), so the multiplies are packed (FMUL2) and each add that consumes a product stays scalar.
+__device__ __forceinline__ unsigned long long pk(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long pk_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pk_add(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long pk_add_scalar(unsigned long long a, float c) {  // never fused with a producer
+    float x, y;
+    unpk(a, x, y);
+    return pk(__fadd_rn(x, c), __fadd_rn(y, c));
+}
+__device__ __forceinline__ void quantize2_biased(float p0, float p1, float bias, int &t0, int &t1) {
+    const unsigned b0 = __float_as_uint(p0), b1 = __float_as_uint(p1);
+    const unsigned long long lv = pk_add(pk(exponent_as_float(b0), exponent_as_float(b1)), pk(-bias, -bias));
+    const unsigned long long m = pk(mantissa_1_2(b0), mantissa_1_2(b1));
+    unsigned long long t = pk_mul(pk(-0.34484843f, -0.34484843f), m);
+    t = pk_add_scalar(t, 2.02466578f);
+    t = pk_mul(t, m);
+    t = pk_add_scalar(t, -0.67487759f);
+    unsigned long long v = pk_add(lv, t);  // both operands are sums: nothing to contract
+    v = pk_mul(v, pk(0.3010299956639812f, 0.3010299956639812f));
+    v = pk_mul(v, pk(20.f, 20.f));
+    float vx, vy;
+    unpk(v, vx, vy);
+    t0 = __float2int_rz(fmaxf(__fadd_rn(vx, 127.f), -128.f));
+    t1 = __float2int_rz(fmaxf(__fadd_rn(vy, 127.f), -128.f));
+}
+// CNT bins of one level -> little-endian packed bytes in w[(CNT+3)/4]
+template <int CNT, bool PK> __device__ __forceinline__ void quantize_pack(const float *pw, float bias, unsigned *w) {
+    int t[CNT];
+    if constexpr (PK && CNT >= 2) {
+#pragma unroll
+        for (int i = 0; i < CNT; i += 2) quantize2_biased(pw[i], pw[i + 1], bias, t[i], t[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) t[i] = quantize_biased(pw[i], bias);
+    }
+    if constexpr (CNT >= 4) {
+#pragma unroll
+        for (int i = 0; i < CNT / 4; i++)
+            w[i] = __byte_perm(__byte_perm(t[4 * i], t[4 * i + 1], 0x0040), __byte_perm(t[4 * i + 2], t[4 * i + 3], 0x0040), 0x5410);
+    } else if constexpr (CNT == 2) {
+        w[0] = __byte_perm(t[0], t[1], 0x0040) & 0xFFFFu;
+    } else {
+        w[0] = (unsigned)t[0] & 0xFFu;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,26 +422,48 @@ struct PyrParams {
 // grid ((R >> base_level) / (256*PER), frames), block 256: each thread owns PER (4 or 16) consecutive entries of the
 // base level; the block then reduces log2(PER) levels in registers, five with warp shuffles and three through
 // shared memory (pairwise sums, src/fft_impl.cpp:45-61,162-172) - log2(PER) + 8 levels above the base in all.
-template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
     static_assert(PER == 4 || PER == 16, "PER must be 4 or 16");
     constexpr int LP = (PER == 16) ? 4 : 2;  // levels reduced in registers
     __shared__ float warp_sum_s[8];
     const int tid = threadIdx.x;
     const int frame = blockIdx.y;
-    const size_t R = (size_t)1 << p.log2R;
+    const unsigned R = 1u << p.log2R;  // bins and pyramid offsets fit 32 bits (R <= 2^23)
     const int B = (MODE == PYR_SCRATCH) ? p.base_level : 0;
-    const size_t d0 = ((size_t)blockIdx.x * 256 + tid) * PER;  // index at level B
+    const unsigned d0 = (blockIdx.x * 256u + tid) * PER;  // index at level B
     int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
 
     float pw[PER];
     if constexpr (MODE == PYR_SPEC) {
         // display bin d <-> FFT bin (d + R/2 + 1) mod R   (src/fft_impl.cpp:148-160)
         const float2 *spec = p.spec + (size_t)frame * p.spec_stride;
+        const unsigned k0 = (d0 + (R >> 1) + 1) & (R - 1);
+        // d0 is a multiple of PER, so the thread's PER bins start at k0 == 1 (mod PER): with the engine's buffer offset
+        // (bin 1 on a 128-byte line) that is an aligned, contiguous run - 128-bit loads, except for the one thread
+        // whose run wraps past bin R-1 and for externally bound, unaligned buffers
+        if (k0 + PER <= R && (reinterpret_cast<uintptr_t>(spec + k0) & 15) == 0) {
+            const float4 *src = reinterpret_cast<const float4 *>(spec + k0);
 #pragma unroll
-        for (int i = 0; i < PER; i++) {
-            const size_t k = (d0 + i + (R >> 1) + 1) & (R - 1);
-            const float2 x = spec[k];
-            pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+            for (int i = 0; i < PER / 2; i++) {
+                const float4 x = src[i];
+                if constexpr (PK) {  // (re^2, im^2) in one FMUL2, then the separately rounded sum
+                    float a, b, c, d;
+                    const unsigned long long v0 = pk(x.x, x.y), v1 = pk(x.z, x.w);
+                    unpk(pk_mul(v0, v0), a, b);
+                    unpk(pk_mul(v1, v1), c, d);
+                    pw[2 * i] = __fadd_rn(a, b);
+                    pw[2 * i + 1] = __fadd_rn(c, d);
+                } else {
+                    pw[2 * i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+                    pw[2 * i + 1] = __fadd_rn(__fmul_rn(x.z, x.z), __fmul_rn(x.w, x.w));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const float2 x = spec[(k0 + i) & (R - 1)];
+                pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+            }
         }
     } else if constexpr (MODE == PYR_R2C) {
         // r2c split: X[k] = (Z[k] + conj(Z[M-k]))/2 - (i/2) W_size^k (Z[k] - conj(Z[M-k])), M = R
@@ -374,7 +471,7 @@ template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kern
         const float2 *Z = p.Z + (size_t)frame * R;
 #pragma unroll
         for (int i = 0; i < PER; i++) {
-            const size_t k = d0 + i;
+            const unsigned k = d0 + i;
             const float2 a = Z[k];
             const float2 b = Z[(R - k) & (R - 1)];
             const float2 e = make_float2(a.x + b.x, a.y - b.y);
@@ -398,9 +495,9 @@ template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kern
     } else if constexpr (MODE == PYR_POWER) {
         // |X|^2 left by FFT pass 2 in [u2][u1] order: display bin d = u1 + N1 * ((u2 + N2/2) mod N2)
         const int N1 = p.ntiles, N2 = p.N2;  // (ntiles carries N1 in this mode)
-        const size_t u1 = d0 & (size_t)(N1 - 1), d2 = d0 / N1;
-        const size_t u2 = (d2 + (N2 >> 1)) & (size_t)(N2 - 1);
-        const float4 *src = reinterpret_cast<const float4 *>(p.pscratch + (size_t)frame * R + u2 * N1 + u1);
+        const unsigned u1 = d0 & (unsigned)(N1 - 1), d2 = d0 / (unsigned)N1;
+        const unsigned u2 = (d2 + (N2 >> 1)) & (unsigned)(N2 - 1);
+        const float4 *src = reinterpret_cast<const float4 *>(p.pscratch + (size_t)frame * R + (size_t)(u2 * N1 + u1));
 #pragma unroll
         for (int i = 0; i < PER / 4; i++) {
             const float4 f = src[i];
@@ -413,16 +510,16 @@ template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kern
         const float *scr = p.pscratch + (size_t)frame * p.ntiles * p.N2;
 #pragma unroll
         for (int i = 0; i < PER; i++) {
-            const size_t idx = d0 + i;
-            const size_t tile = idx % p.ntiles, d2 = idx / p.ntiles;
+            const unsigned idx = d0 + i;
+            const unsigned tile = idx % (unsigned)p.ntiles, d2 = idx / (unsigned)p.ntiles;
             pw[i] = scr[tile * p.N2 + d2];
         }
     }
     const int L = p.levels - B;  // levels still to produce, counted from the base
     const int off = p.size_log2 - B;
-    size_t lvl_off = 0;          // byte offset of level B
+    unsigned lvl_off = 0;        // byte offset of level B
     for (int i = 0; i < B; i++) lvl_off += R >> i;
-    const size_t RB_ = R >> B;   // entries at the base level
+    const unsigned RB_ = R >> B;   // entries at the base level
     if (L <= 0) return;
     // relative levels 0 .. LP in registers: level lv has PER >> lv values per thread, stored as one word/vector
     static_for<LP + 1>([&](auto lvc) {
@@ -430,10 +527,7 @@ template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kern
         constexpr int CNT = PER >> lv;
         if (lv < L) {
             unsigned w[(CNT + 3) / 4];
-#pragma unroll
-            for (int i = 0; i < (CNT + 3) / 4; i++) w[i] = 0;
-#pragma unroll
-            for (int i = 0; i < CNT; i++) w[i / 4] |= (unsigned)quantize_dev(pw[i], off - lv) << (8 * (i % 4));
+            quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w);
             store_packed<CNT>(quant + lvl_off + (d0 >> lv), w);
         }
         lvl_off += RB_ >> lv;
@@ -460,14 +554,14 @@ template <int MODE, int PER> __global__ void __launch_bounds__(256) pyramid_kern
             __syncthreads();
             if (tid < 8) {
                 float w = warp_sum_s[tid];
-                const size_t b0 = (size_t)blockIdx.x * 256 * PER;
+                const unsigned b0 = blockIdx.x * 256u * PER;
 #pragma unroll
                 for (int k = 1; k <= 3; k++) {  // relative levels LP+6 .. LP+8 across the eight warps
                     const int lv = LP + 5 + k;
                     if (lv < L) {
                         w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (k - 1)));
                         if ((tid & ((1 << k) - 1)) == 0)
-                            quant[lvl_off + ((b0 + (size_t)32 * PER * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
+                            quant[lvl_off + ((b0 + 32u * PER * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
                         lvl_off += RB_ >> lv;
                     }
                 }

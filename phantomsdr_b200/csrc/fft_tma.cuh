@@ -31,18 +31,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// try_wait suspends for a hardware-defined time slice per attempt; a transfer that never lands (a bug) traps after
+// ~2^22 attempts instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+        if (spins > (1u << 22)) __trap();
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -85,7 +91,7 @@ static_assert(TmaSmem::kStage >= sizeof(float2) * 32 * TmaSmem::kRow2, "stage mu
 template <bool REAL>
 __global__ void __launch_bounds__(kTmaThreads, 2)
     fft_pass1_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap ring_map,
-                         const __grid_constant__ CUtensorMap window_map, int nframes, int nsplit) {
+                         const __grid_constant__ CUtensorMap window_map, int nframes, int order, int nsplit) {
     constexpr int T = kTmaT, RA = 32, RB = 32, N1 = kS, N2 = kS;
     constexpr int SHIFT = REAL ? 0 : 1;
     constexpr int ROW = TmaSmem::kRow1;
@@ -97,9 +103,40 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
                                                   (REAL ? TmaSmem::kWindowR : TmaSmem::kWindowC));
     uint64_t *full = bars, *wbar = bars + 1;
 
+    // Work items (column tile, frame) of this CTA, item j = 0 .. nitems-1:
+    //   order 0: CTA (tile, part) keeps ONE column tile (window slice and twiddles loaded once) and takes the frames
+    //            f == part (mod nsplit); all CTAs sweep the batch frame by frame together, so the hop reads and the Y
+    //            writes of neighbouring column tiles coalesce in L2 / DRAM pages
+    //   order 1: tile-major list cut into gridDim.x equal contiguous chunks (balanced, but the CTAs are spread over
+    //            all frames of the batch at any instant: measured slower, DRAM page locality is lost)
+    //   order 2: frame-major list cut into equal contiguous chunks (balanced and frame-synchronous; the window slice
+    //            and the twiddles change with every item)
     const int tid = threadIdx.x;
-    const int tile = blockIdx.x / nsplit;
-    const int part = blockIdx.x - tile * nsplit;
+    constexpr int NT = N2 / T;
+    int begin = 0, nitems = 0;
+    if (order == 0) {
+        begin = (int)blockIdx.x;  // tile * nsplit + part
+        const int part = (int)blockIdx.x % nsplit;
+        nitems = part < nframes ? (nframes - part + nsplit - 1) / nsplit : 0;
+    } else {
+        const int total = NT * nframes;
+        const int per = total / (int)gridDim.x, rem = total % (int)gridDim.x;
+        begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+        nitems = per + ((int)blockIdx.x < rem ? 1 : 0);
+    }
+    if (nitems <= 0) return;
+    auto item_of = [&](int j, int &tile, int &f) {
+        if (order == 0) {
+            tile = begin / nsplit;
+            f = begin % nsplit + j * nsplit;
+        } else if (order == 1) {
+            tile = (begin + j) / nframes;
+            f = (begin + j) - tile * nframes;
+        } else {
+            f = (begin + j) / NT;
+            tile = (begin + j) - f * NT;
+        }
+    };
     if (tid == 0) {
         mbar_init(full, 1);
         mbar_init(wbar, 1);
@@ -109,8 +146,8 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
     for (int i = tid; i < 32 * 32; i += kTmaThreads) twA[i] = p.twA1[i];
     __syncthreads();
 
-    // thread 0 drives TMA: the window slice once, then one tile ahead of the consumers
-    auto issue_tile = [&](int f) {
+    // thread 0 drives TMA: the window slice of a column tile when it changes, and one item ahead of the consumers
+    auto issue_item = [&](int tile, int f) {
         mbar_expect_tx(full, sizeof(float2) * N1 * T);
         const int hopA = (p.hop0 + f) % p.nhops, hopB = (p.hop0 + f + 1) % p.nhops;
         // rows 0..511 of the frame come from the older hop, 512..1023 from the newer one
@@ -119,37 +156,46 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
         tma_load_2d(smem_raw + 2 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2), full);
         tma_load_2d(smem_raw + 3 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2) + 256, full);
     };
-    if (tid == 0) {
+    auto issue_window = [&](int tile) {
         constexpr uint32_t kWinBytes = sizeof(float) * N1 * T * (REAL ? 2 : 1);
         mbar_expect_tx(wbar, kWinBytes);
         for (int b = 0; b < 4; b++)
             tma_load_2d(reinterpret_cast<unsigned char *>(win) + b * (kWinBytes / 4), &window_map, tile * T * (REAL ? 2 : 1),
                         b * 256, wbar);
-        if (part < nframes) issue_tile(part);
+    };
+    if (tid == 0) {
+        int tile0, f0;
+        item_of(0, tile0, f0);
+        issue_window(tile0);
+        issue_item(tile0, f0);
     }
 
     // ===== consumers =====
     const int c = tid % T;
     const int r = tid / T;
     const int q = r;
-    const int n2 = tile * T + c;
     const size_t M = (size_t)N1 * N2;
     // inter-pass twiddles of this thread, W_M^(n2*k1) for k1 = q + 32 s with s = 4a + b:
     //   G[a] = W_M^(n2*(q + 128 a)),  B[b-1] = W_M^(32*n2*b)   ->   tw(s) = G[a] * B[b-1]  (b = 0: G[a])
     // (the IQ k1 = 0 row, q = 0 and s = 0, carries the one-slot rotation W_M^(N1*n2) instead)
-    float2 G[8], B[3];
-    {
-        auto tw_lookup = [&](unsigned e) { return cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + ((e >> 10) & 1023u))); };
+    float2 G[8], B[3], rot0;
+    auto tw_lookup = [&](unsigned e) { return cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + ((e >> 10) & 1023u))); };
+    int cur_tile = -1, wphase = 0;
+    for (int it_local = 0; it_local < nitems; it_local++) {
+        int tile, f;
+        item_of(it_local, tile, f);
+        const int n2 = tile * T + c;
+        if (tile != cur_tile) {  // (CTA-uniform) new column tile: its twiddles and its slice of the Hann window
+            cur_tile = tile;
 #pragma unroll
-        for (int a = 0; a < 8; a++) G[a] = tw_lookup((unsigned)n2 * (unsigned)(q + 128 * a));
+            for (int a = 0; a < 8; a++) G[a] = tw_lookup((unsigned)n2 * (unsigned)(q + 128 * a));
 #pragma unroll
-        for (int b = 1; b < 4; b++) B[b - 1] = tw_lookup((unsigned)n2 * 32u * (unsigned)b);
-    }
-    const float2 rot0 = cmul(__ldg(p.TL + (((unsigned)N1 * (unsigned)n2) & 1023u)), __ldg(p.TH + (((unsigned)N1 * (unsigned)n2) >> 10)));
-    mbar_wait(wbar, 0);
-    int it = 0;
-    for (int f = part; f < nframes; f += nsplit, it++) {
-        mbar_wait(full, it & 1);
+            for (int b = 1; b < 4; b++) B[b - 1] = tw_lookup((unsigned)n2 * 32u * (unsigned)b);
+            rot0 = tw_lookup((unsigned)N1 * (unsigned)n2);
+            mbar_wait(wbar, wphase & 1);
+            wphase++;
+        }
+        mbar_wait(full, it_local & 1);
         float2 v[RA];
 #pragma unroll
         for (int j = 0; j < RA; j++) {
@@ -174,10 +220,13 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
         float2 u[RB];
 #pragma unroll
         for (int rr = 0; rr < RB; rr++) u[rr] = sm[rr * ROW + q * T + c];
-        consumer_sync();  // exchange consumed: the next tile streams in while this one is finished
-        if (tid == 0 && f + nsplit < nframes) {
-            fence_proxy_async();  // generic-proxy accesses to the stage are ordered before the TMA write
-            issue_tile(f + nsplit);
+        consumer_sync();  // exchange consumed: the next item streams in while this one is finished
+        if (tid == 0 && it_local + 1 < nitems) {
+            fence_proxy_async();  // generic-proxy accesses to the stage / window are ordered before the TMA writes
+            int ntile, nf;
+            item_of(it_local + 1, ntile, nf);
+            if (ntile != tile) issue_window(ntile);  // every thread finished reading the old slice before the first sync
+            issue_item(ntile, nf);
         }
         RegDft<RB>::run(u);
         float2 *Y = p.Y + (size_t)f * M + n2;
@@ -319,6 +368,144 @@ __global__ void __launch_bounds__(kTmaThreads, 2) fft_pass2_tma_kernel(const Fwd
                     for (int k = 0; k < CNT / 2; k++) vv[k] = __fadd_rn(vv[2 * k], vv[2 * k + 1]);
                 });
                 scr[d2] = vv[0];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2, three-stage variant: ONE CTA per SM, two consumer groups of eight warps, three 64 KiB stages.
+// Tile j of the CTA (j = 0, 1, 2, ...; global tile blockIdx.x + j*gridDim.x) is handled by group j % 2 in
+// stage j % 3. A group hands its stage back as soon as its exchange is consumed and immediately streams tile
+// j + 3 into it (which the OTHER group will consume), so every tile has a whole iteration of lead time and
+// the SM always has 64-128 KiB of loads in flight - same 16 warps per SM as the two-CTA variant, twice the
+// memory-level parallelism. The 1/N scale is folded into the (power-of-two scaled, hence bit-identical)
+// intra-pass twiddles; spectrum / power addresses are one base pointer + compile-time offsets.
+// ------------------------------------------------------------------------------------------------
+constexpr int kP3Groups = 2;
+constexpr int kP3Threads = kP3Groups * kTmaThreads;   // 512
+constexpr int kP3Stages = 3;
+struct P3Smem {
+    static constexpr size_t kStage = sizeof(float2) * 32 * TmaSmem::kRow2;   // 65 792 B: raw tile (64 KiB) or exchange
+    static constexpr size_t kTw = sizeof(float2) * 32 * 32;
+    static constexpr size_t kTotal = kP3Stages * kStage + kTw + 64;
+};
+static_assert(P3Smem::kStage % 16 == 0, "stage must stay 16-byte aligned for bulk copies");
+static_assert(P3Smem::kTotal <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
+
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kTmaThreads) : "memory");
+}
+
+template <int FUSE, bool PEERS>
+__global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const FwdParams p, int nframes) {
+    constexpr int T = kTmaT, RA = 32, RB = 32, N1 = kS, N2 = kS;
+    constexpr int ROW = TmaSmem::kRow2;
+    static_assert(FUSE == 0 || FUSE == 2, "the three-stage kernel has no room for the in-kernel waterfall epilogue");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    float2 *twA = reinterpret_cast<float2 *>(smem_raw + kP3Stages * P3Smem::kStage);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kP3Stages * P3Smem::kStage + P3Smem::kTw);
+
+    const int tid = threadIdx.x;
+    const int g = tid / kTmaThreads;       // consumer group
+    const int gt = tid - g * kTmaThreads;  // thread within the group
+    const int tiles_per_frame = N1 / T;
+    const int total = tiles_per_frame * nframes;
+    const size_t M = (size_t)N1 * N2;
+    if (tid == 0) {
+        for (int s = 0; s < kP3Stages; s++) mbar_init(full + s, 1);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    const float scale = p.scale;
+    for (int i = tid; i < 32 * 32; i += kP3Threads) {
+        const float2 w = p.twA2[i];
+        twA[i] = make_float2(w.x * scale, w.y * scale);  // scale = 2^-k: exact, commutes with every later rounding
+    }
+    __syncthreads();
+    auto issue_tile = [&](int j) {  // T consecutive rows of Y are one contiguous 64 KiB block
+        const int i = blockIdx.x + j * gridDim.x;
+        const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
+        const int st = j % kP3Stages;
+        mbar_expect_tx(full + st, sizeof(float2) * N2 * T);
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(p.Y + (size_t)frame * M + (size_t)tile * T * N2);
+        unsigned char *dst = smem_raw + (size_t)st * P3Smem::kStage;
+        for (int k = 0; k < 4; k++) bulk_load_1d(dst + k * 16384, src + k * 16384, 16384, full + st);
+    };
+    if (tid == 0)
+        for (int j = 0; j < kP3Stages; j++)
+            if ((int)blockIdx.x + j * (int)gridDim.x < total) issue_tile(j);
+
+    for (int j = g; (int)blockIdx.x + j * (int)gridDim.x < total; j += kP3Groups) {
+        const int i = blockIdx.x + j * gridDim.x;
+        const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
+        const int st = j % kP3Stages;
+        float2 *sm = reinterpret_cast<float2 *>(smem_raw + (size_t)st * P3Smem::kStage);
+        mbar_wait(full + st, (j / kP3Stages) & 1);
+        {   // stage A: lanes along n2
+            const int r = gt % 32;
+            const int c = gt / 32;
+            float2 v[RA];
+#pragma unroll
+            for (int jj = 0; jj < RA; jj++) v[jj] = sm[c * N2 + r + RB * jj];
+            group_sync(g);
+            RegDft<RA>::run(v);
+            const float2 *tw = twA + r;
+#pragma unroll
+            sm[r * ROW + c] = make_float2(v[0].x * scale, v[0].y * scale);
+#pragma unroll
+            for (int qq = 1; qq < RA; qq++) sm[r * ROW + qq * T + c] = cmul(v[qq], tw[qq * RB]);
+        }
+        group_sync(g);
+        const int c = gt % T;
+        const int q = gt / T;
+        float2 u[RB];
+#pragma unroll
+        for (int rr = 0; rr < RB; rr++) u[rr] = sm[rr * ROW + q * T + c];
+        group_sync(g);  // exchange consumed: the stage is free for tile j + 3
+        if (gt == 0 && (int)blockIdx.x + (j + kP3Stages) * (int)gridDim.x < total) {
+            fence_proxy_async();  // generic-proxy accesses to the stage are ordered before the TMA write
+            issue_tile(j + kP3Stages);
+        }
+        RegDft<RB>::run(u);
+        // bin k = (u1 + N1*u2 + shift) mod M with u2 = q + 32 s: one base pointer, compile-time offsets; the only
+        // wrap is u = M-1 -> k = 0 (IQ), handled by redirecting that single store
+        const unsigned u1 = tile * T + c;
+        float2 *out = p.out + (size_t)frame * p.out_stride;
+        float2 *o = out + u1 + p.shift + (size_t)N1 * q;
+        const bool wraps = p.shift && u1 == N1 - 1 && q == RA - 1;
+#pragma unroll
+        for (int s = 0; s < RB - 1; s++) o[(size_t)N1 * RA * s] = u[s];
+        *(wraps ? out : o + (size_t)N1 * RA * (RB - 1)) = u[RB - 1];
+        if constexpr (FUSE == 2) {
+            float *pp = p.pscratch + (size_t)frame * M + (size_t)q * N1 + u1;
+#pragma unroll
+            for (int s = 0; s < RB; s++)
+                pp[(size_t)N1 * RA * s] = __fadd_rn(__fmul_rn(u[s].x, u[s].x), __fmul_rn(u[s].y, u[s].y));
+        }
+        // IQ wrap tail (src/fft.cpp:96-97): out[M + k] = out[k] for k < additional. k grows with s, so only
+        // threads whose s = 0 bin is inside the tail ever enter.
+        const unsigned k0 = u1 + p.shift + N1 * q;
+        if (k0 < (unsigned)p.additional) {
+#pragma unroll
+            for (int s = 0; s < RB; s++)
+                if (k0 + (unsigned)(N1 * RA * s) < (unsigned)p.additional && !(wraps && s == RB - 1))
+                    o[M + (size_t)N1 * RA * s] = u[s];
+        }
+        if (wraps && p.additional > 0) out[M] = u[RB - 1];
+        if constexpr (PEERS) {  // NVLink peer copies of the frame (multi-GPU ingest rank only)
+            for (int pe = 0; pe < p.npeers; pe++) {
+                float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
+#pragma unroll
+                for (int s = 0; s < RB; s++) {
+                    const unsigned k = (unsigned)(((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1));
+                    if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1]))
+                        po[k] = u[s];
+                    const unsigned kt = (unsigned)M + k;
+                    if (k < (unsigned)p.additional &&
+                        ((kt >= p.peer_lo[pe][0] && kt < p.peer_hi[pe][0]) || (kt >= p.peer_lo[pe][1] && kt < p.peer_hi[pe][1])))
+                        po[kt] = u[s];
+                }
             }
         }
     }

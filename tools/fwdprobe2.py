@@ -1,0 +1,92 @@
+"""Forward-group variants: correctness against the baseline variant (bit-for-bit), then per-stage timings.
+Usage: python tools/fwdprobe2.py [batch]"""
+import sys
+sys.path.insert(0, '.')
+import torch
+from phantomsdr_b200 import SpectrumConfig
+from phantomsdr_b200.backend import (B200FFT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_PACKED_MATH, OPT_FWD_LANES,
+                                     OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER)
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+H = 64
+cfg = SpectrumConfig(sps=35_000_000, fft_size=1 << 20)
+eng = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, 0, 0)
+eng.set_output_additional_size(cfg.audio_fft_size)
+eng.plan_c2c()
+eng.set_hop_ring(H)
+eng.set_batch_frames(F)
+s = torch.cuda.Stream()
+torch.cuda.set_stream(s)
+eng.set_stream(s.cuda_stream)
+ring = torch.as_tensor(eng.device_hop_ring(H), device='cuda')
+ring.normal_(0, 1e-3)
+torch.cuda.synchronize()
+
+DEFAULTS = {OPT_FUSED_PYRAMID: 2, OPT_TMA: 1, OPT_PACKED_MATH: 1, OPT_FWD_LANES: 1, OPT_FWD_SUB_FRAMES: 64, OPT_PASS1_ORDER: 0}
+
+
+def configure(opts):
+    for k, v in {**DEFAULTS, **opts}.items():
+        eng.set_option(k, v)
+
+
+def snapshot():
+    eng.execute_device(3, F)
+    torch.cuda.synchronize()
+    spec = torch.as_tensor(eng.device_spectrum(F), device='cuda').clone()
+    quant = torch.as_tensor(eng.device_quantized(F), device='cuda').clone()
+    return spec, quant
+
+
+def t(mask, reps=10):
+    eng.set_option(OPT_STAGE_MASK, mask)
+    for g in range(H // F):
+        eng.execute_device(g * F, F)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(s)
+    for _ in range(reps):
+        for g in range(H // F):
+            eng.execute_device(g * F, F)
+    b.record(s)
+    torch.cuda.synchronize()
+    eng.set_option(OPT_STAGE_MASK, 7)
+    return a.elapsed_time(b) * 1e3 / (reps * H)
+
+
+VARIANTS = [
+    ("base tma1 scalar-q", {OPT_PACKED_MATH: 0}),
+    ("tma1 packed-q", {}),
+    ("tma2 (3-stage p2)", {OPT_TMA: 2}),
+    ("tma2 order1", {OPT_TMA: 2, OPT_PASS1_ORDER: 1}),
+    ("tma2 order2", {OPT_TMA: 2, OPT_PASS1_ORDER: 2}),
+    ("tma2 fuse0", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0}),
+    ("tma2 fuse0 scalar-q", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_PACKED_MATH: 0}),
+    ("tma2 f2 L2 s4", {OPT_TMA: 2, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
+    ("tma2 f0 L2 s4", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
+    ("tma2 f0 L2 s2", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 2}),
+    ("tma2 f0 L3 s2", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 3, OPT_FWD_SUB_FRAMES: 2}),
+    ("tma2 f0 L3 s4", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 3, OPT_FWD_SUB_FRAMES: 4}),
+    ("tma2 f0 L4 s4", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 4, OPT_FWD_SUB_FRAMES: 4}),
+    ("tma2 f0 L2 s8", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 8}),
+    ("tma2 f0 L2 s4 o2", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4, OPT_PASS1_ORDER: 2}),
+    ("tma1 f0 L2 s4", {OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
+]
+ref = None
+for name, opts in VARIANTS:
+    if F < 16 and opts.get(OPT_FWD_SUB_FRAMES, 64) * opts.get(OPT_FWD_LANES, 1) > F:
+        continue
+    configure(opts)
+    spec, quant = snapshot()
+    if ref is None:
+        ref = (spec, quant)
+        chk = "reference"
+    else:
+        ds = (spec - ref[0]).abs().max().item()
+        nq = (quant != ref[1]).sum().item()
+        chk = f"spec maxdiff {ds:.3e} (max {ref[0].abs().max().item():.3e})  pyramid bytes differing {nq}"
+    full = len(opts) == 0 or OPT_FWD_LANES not in opts and OPT_FWD_SUB_FRAMES not in opts
+    if full:
+        print(f"{name:20s} batch {F}: pass1 {t(1):.2f}  pass2 {t(2):.2f}  pyramid {t(4):.2f}  all {t(7):.2f} us/frame | {chk}", flush=True)
+    else:
+        print(f"{name:20s} batch {F}: all {t(7):.2f} us/frame | {chk}", flush=True)
