@@ -52,12 +52,12 @@ def parse_args():
     ap.add_argument("--real", action="store_true", help="r2c input (cfg 3 shape)")
     ap.add_argument("--clients", type=int, default=1024, help="demod clients per GPU")
     ap.add_argument("--ring", type=int, default=64, help="hops resident in HBM = frames per step")
-    ap.add_argument("--batch", type=int, default=16, help="frames per kernel launch")
+    ap.add_argument("--batch", type=int, default=64, help="frames per kernel launch group")
     ap.add_argument("--banks", type=int, default=2, help="pipeline depth: clients of batch k overlap the FFT of batch k+1")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-frames", type=int, default=256)
+    ap.add_argument("--e2e-frames", type=int, default=768)
     ap.add_argument("--mgpu-mode", default="scatter-dma", choices=["spectrum", "scatter", "scatter-dma"],
                     help="N>1 exchange step. spectrum: NCCL broadcast of every spectrum batch (north_star's wording). scatter: "
                          "clients partitioned in (l, r) order and FFT pass 2 on the ingest rank stores each rank's sub-band "
@@ -313,7 +313,8 @@ def run_b200(args):
     eng = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, cfg.brightness_offset, device=local)
     eng.set_output_additional_size(n)
     eng.plan_r2c() if cfg.is_real else eng.plan_c2c()
-    eng.set_hop_ring(H)
+    HR = max(H, 2 * F + 2)  # the block-streaming e2e path keeps two blocks of halves (+ the shared older half) resident
+    eng.set_hop_ring(HR)
     eng.set_batch_frames(F)
     eng.set_pipeline(args.banks)
     eng.clients_create(args.clients, n, cfg.audio_sps)
@@ -333,7 +334,7 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
 
-    ring_t = torch.as_tensor(eng.device_hop_ring(H), device=dev)
+    ring_t = torch.as_tensor(eng.device_hop_ring(HR), device=dev)
     spec_banks = []
     for b in range(args.banks):
         eng.select_bank(b)

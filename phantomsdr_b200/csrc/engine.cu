@@ -87,6 +87,8 @@ std::vector<float2> tw_pow(size_t count, size_t mult, size_t N) {  // [j] = exp(
 
 }  // namespace
 
+extern "C" int b200_set_option(struct b200_engine *e, int option, int value);
+
 struct b200_engine {
     int device = 0;
     size_t size = 0;
@@ -97,6 +99,9 @@ struct b200_engine {
     bool is_real = false;
     size_t M = 0;  // complex transform length
     int log2M = 0;
+    int na = 1;        // M = na * Mb: radix-na split in front of na two-pass sub-transforms (M > 2^20)
+    int log2Mb = 0;    // sub-transform length (== log2M when na == 1)
+    float2 *d_pre = nullptr, *d_TLM = nullptr, *d_THM = nullptr;
     size_t R = 0;  // fft_result_size
     SubPlan sp1{}, sp2{};
     cudaStream_t stream = nullptr;      // the stream forward work is enqueued on
@@ -197,17 +202,17 @@ struct b200_engine {
 
 namespace {
 
-template <int RA, int RB, int T, bool RAW, bool REAL> int launch_pass1r(b200_engine *e, const FwdParams &p, int frames) {
+template <int RA, int RB, int T, bool RAW, bool REAL, bool PRE = false> int launch_pass1r(b200_engine *e, const FwdParams &p, int frames) {
     constexpr int threads = T * CMax<RA, RB>::v;
     constexpr int PAD = (T < 16) ? (16 - T) : 0;
     constexpr size_t smem = sizeof(float2) * RB * (RA * T + PAD);
     if (frames == 0) {  // preparation call from plan time
-        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T, RAW, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CU(cudaFuncSetAttribute(fft_pass1_kernel<RA, RB, T, RAW, REAL, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
         return 0;
     }
     dim3 grid(p.N2 / T, frames);
-    fft_pass1_kernel<RA, RB, T, RAW, REAL><<<grid, threads, smem, e->stream>>>(p);
+    fft_pass1_kernel<RA, RB, T, RAW, REAL, PRE><<<grid, threads, smem, e->stream>>>(p);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -369,6 +374,24 @@ int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse) {
     return 0;
 }
 
+template <int NA> int launch_split_na(b200_engine *e, const FwdParams &p, int frames) {
+    dim3 grid((unsigned)(((size_t)1 << e->log2Mb) / 256), frames);
+    float2 *pre = const_cast<float2 *>(p.pre);
+    if (e->is_real) radix_split_kernel<NA, true><<<grid, 256, 0, e->stream>>>(p, pre, e->d_TLM, e->d_THM, e->log2Mb);
+    else radix_split_kernel<NA, false><<<grid, 256, 0, e->stream>>>(p, pre, e->d_TLM, e->d_THM, e->log2Mb);
+    e->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+int launch_split(b200_engine *e, const FwdParams &p, int frames) {
+    switch (e->na) {
+    case 2: return launch_split_na<2>(e, p, frames);
+    case 4: return launch_split_na<4>(e, p, frames);
+    case 8: return launch_split_na<8>(e, p, frames);
+    }
+    return fail(B200_ENOTSUP, "no radix-%d split kernel", e->na);
+}
+
 int bank_acquire(b200_engine *e) {
     // the forward stream may only overwrite a bank once the clients that read it are done
     if (e->banks > 1 && e->cli_pending[e->cur_bank]) {
@@ -393,7 +416,9 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     p.in_format = e->in_format;
     p.window = e->d_window;
     p.Y = e->d_Y + slot0 * e->M;
-    p.log2M = e->log2M;
+    p.na = e->na;
+    p.pre = e->na > 1 ? e->d_pre + slot0 * e->M : nullptr;
+    p.log2M = e->log2Mb;  // what passes 1 and 2 transform (the sub-transform when na > 1)
     p.N1 = e->sp1.S;
     p.N2 = e->sp2.S;
     p.is_real = e->is_real ? 1 : 0;
@@ -403,7 +428,7 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     p.TH = e->d_TH;
     float2 *spec = e->spec_ptr() + (size_t)f0 * e->spec_stride;
     if (!e->is_real) {
-        p.shift = 1;
+        p.shift = e->na > 1 ? 0 : 1;  // the display-aligned row order only exists in the plain two-pass transform
         p.out = spec;
         p.out_stride = e->spec_stride;
         p.scale = 1.0f / (float)e->size;
@@ -426,7 +451,7 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         p.npeers = 0;
     }
     // 0 none (pyramid kernel re-reads the spectrum), 1 full epilogue in pass 2, 2 |X|^2 plane from pass 2
-    const int fuse = e->is_real ? 0 : (e->opt_fused_pyramid >= 0 ? e->opt_fused_pyramid : (tma_path(e) ? 0 : 2));
+    const int fuse = (e->is_real || e->na > 1) ? 0 : (e->opt_fused_pyramid >= 0 ? e->opt_fused_pyramid : (tma_path(e) ? 0 : 2));
     int base_level = 0;
     while ((1 << base_level) < e->sp2.T) base_level++;
     int8_t *quant = e->quant_ptr() + (size_t)f0 * e->pyr_stride;
@@ -442,10 +467,20 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         base_level = 0;
         while ((1 << base_level) < kTmaT) base_level++;
     }
-    if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
-    if (rc) return rc;
-    if (e->opt_stage_mask & 2) rc = tma ? launch_tma_pass2(e, p, frames, fuse) : dispatch_pass2(e, p, frames, fuse);
-    if (rc) return rc;
+    if (e->na > 1) {
+        if (e->opt_stage_mask & 1) {
+            rc = launch_split(e, p, frames);
+            if (!rc) rc = launch_pass1r<32, 32, 16, false, true, true>(e, p, frames * e->na);
+        }
+        if (rc) return rc;
+        if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames * e->na, 0);
+        if (rc) return rc;
+    } else {
+        if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
+        if (rc) return rc;
+        if (e->opt_stage_mask & 2) rc = tma ? launch_tma_pass2(e, p, frames, fuse) : dispatch_pass2(e, p, frames, fuse);
+        if (rc) return rc;
+    }
     if (!(e->opt_stage_mask & 4)) return 0;
 
     PyrParams q{};
@@ -560,10 +595,14 @@ int plan_common(b200_engine *e, bool is_real) {
     case 18: s1 = 512; s2 = 512; break;
     case 19: s1 = 1024; s2 = 512; break;
     case 20: s1 = 1024; s2 = 1024; break;
+    case 21: case 22: case 23: s1 = 1024; s2 = 1024; break;  // radix-2/4/8 split + 2^20-point sub-transforms
     default:
-        return fail(B200_ENOTSUP, "fft size %zu (%s) not supported: complex transform length must be 2^16..2^20", e->size,
+        return fail(B200_ENOTSUP, "fft size %zu (%s) not supported: complex transform length must be 2^16..2^23", e->size,
                     is_real ? "r2c" : "c2c");
     }
+    e->log2Mb = std::min(e->log2M, 20);
+    e->na = 1 << (e->log2M - e->log2Mb);
+    const size_t Mb = (size_t)1 << e->log2Mb;
     e->sp1 = sub_plan(s1, "B200_TILE1");
     e->sp2 = sub_plan(s2, "B200_TILE2");
     if (e->levels < 1) return fail(B200_EINVAL, "downsample_levels must be >= 1");
@@ -577,8 +616,13 @@ int plan_common(b200_engine *e, bool is_real) {
     // twiddles (double precision on the host, rounded once)
     e->d_twA1 = upload_f2(tw_sub(e->sp1.RA, e->sp1.RB));
     e->d_twA2 = upload_f2(tw_sub(e->sp2.RA, e->sp2.RB));
-    e->d_TL = upload_f2(tw_pow(1024, 1, e->M));
-    e->d_TH = upload_f2(tw_pow(std::max<size_t>(1, e->M / 1024), 1024, e->M));
+    e->d_TL = upload_f2(tw_pow(1024, 1, Mb));
+    e->d_TH = upload_f2(tw_pow(std::max<size_t>(1, Mb / 1024), 1024, Mb));
+    if (e->na > 1) {
+        e->d_TLM = upload_f2(tw_pow(1024, 1, e->M));
+        e->d_THM = upload_f2(tw_pow(e->M / 1024, 1024, e->M));
+        if (!e->d_TLM || !e->d_THM) return fail(B200_ENOMEM, "twiddle allocation failed");
+    }
     if (is_real) {
         e->d_TLr = upload_f2(tw_pow(1024, 1, e->size));
         e->d_THr = upload_f2(tw_pow(std::max<size_t>(1, e->M / 1024), 1024, e->size));
@@ -597,12 +641,22 @@ int plan_common(b200_engine *e, bool is_real) {
         if (rc) return rc;
         rc = dispatch_pass2(e, none, 0, false);
         if (rc) return rc;
+        if (e->na > 1) rc = launch_pass1r<32, 32, 16, false, true, true>(e, none, 0);
+        if (rc) return rc;
     }
     {
         int rc = tma_prepare(e);
         if (rc) return rc;
     }
     e->planned = true;
+    if (const char *opts = getenv("B200_OPTS")) {  // tuning aid: "option=value,option=value" applied after planning
+        int k = 0, v = 0, used = 0;
+        while (sscanf(opts, "%d=%d%n", &k, &v, &used) == 2) {
+            b200_set_option(e, k, v);
+            opts += used;
+            if (*opts == ',') opts++;
+        }
+    }
     return 0;
 }
 
@@ -619,6 +673,9 @@ int alloc_batch(b200_engine *e, int frames) {
     e->d_quant = nullptr;
     e->d_ptop = nullptr;
     CU(cudaMalloc(&e->d_Y, sizeof(float2) * e->M * frames));
+    if (e->d_pre) cudaFree(e->d_pre);
+    e->d_pre = nullptr;
+    if (e->na > 1) CU(cudaMalloc(&e->d_pre, sizeof(float2) * e->M * frames));
     if (e->is_real) CU(cudaMalloc(&e->d_Z, sizeof(float2) * e->M * frames));
     // IQ bins are stored in runs k = 8m+1 .. 8m+8 (display shift, fft_impl.cpp:148-160): offsetting the buffer by 15
     // elements makes every run start on a 64-byte boundary, so pass 2 writes whole sectors

@@ -55,6 +55,11 @@ struct FwdParams {
     float *pscratch;         // [frames][N1/T][N2] power sums of level log2(T)
     int levels;
     int size_log2;
+    // transforms longer than 2^20 points: M = na * Mb. radix_split_kernel leaves na sub-sequences of Mb points in `pre`
+    // (windowed, radix-na butterflies and W_M twiddles applied); passes 1 and 2 then run na sub-transforms per frame
+    // and pass 2 interleaves their bins, k = ka + na * k_sub
+    const float2 *pre;       // [frames][na][Mb]
+    int na;                  // 1 = plain two-pass transform
 };
 
 template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
@@ -81,9 +86,10 @@ __device__ __forceinline__ float2 load_sample(const void *hop, int fmt, size_t e
 // ------------------------------------------------------------------------------------------------
 // pass 1: grid (N2/T, frames), block T*max(RA,RB)
 // ------------------------------------------------------------------------------------------------
-template <int RA, int RB, int T, bool RAW, bool REAL>
+template <int RA, int RB, int T, bool RAW, bool REAL, bool PRE = false>
 __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const FwdParams p) {
-    constexpr int SHIFT = REAL ? 0 : 1;  // the IQ display shift exists only for c2c (fft_impl.cpp:148-150)
+    // the IQ display shift exists only for c2c (fft_impl.cpp:148-150) and only when pass 2 owns display-aligned runs
+    constexpr int SHIFT = (REAL || PRE) ? 0 : 1;
     constexpr int PAD = (T < 16) ? (16 - T) : 0;   // keep the two r-rows of a half-warp on disjoint banks
     constexpr int ROW = RA * T + PAD;
     extern __shared__ float2 sm[];
@@ -108,8 +114,11 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
         for (int j = 0; j < RA; j++) {
             const size_t idx = (size_t)(r + RB * j) * N2 + n2;  // complex element within the frame
             // first half of the frame (j < RA/2) comes from the older hop
-            float2 x = (j < RA / 2) ? load_sample(hopA, fmt, idx) : load_sample(hopB, fmt, idx - half);
-            if constexpr (REAL) {
+            float2 x;
+            if constexpr (PRE) x = p.pre[(size_t)frame * M + idx];  // sub-sequence `frame` of radix_split_kernel, already windowed
+            else x = (j < RA / 2) ? load_sample(hopA, fmt, idx) : load_sample(hopB, fmt, idx - half);
+            if constexpr (PRE) {
+            } else if constexpr (REAL) {
                 float2 w = __ldg(reinterpret_cast<const float2 *>(p.window) + idx);
                 x.x *= w.x;
                 x.y *= w.y;
@@ -146,6 +155,48 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass1_kernel(const Fwd
             const float2 tw = cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + (e >> 10)));
             Y[(size_t)u1 * N2 + n2] = cmul(u[s], tw);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// transforms longer than 2^20 points, M = NA * Mb with n = Mb*na + nb and k = ka + NA*kb:
+//   A_ka[nb] = W_M^(nb*ka) * sum_na w[n] x[n] W_NA^(na*ka)        (this kernel: fully coalesced, window + sample
+//   X[ka + NA*kb] = DFT_Mb(A_ka)[kb]                               conversion fused; then NA two-pass sub-transforms)
+// grid (Mb / 256, frames), block 256: one thread per nb.
+// ------------------------------------------------------------------------------------------------
+template <int NA, bool REAL>
+__global__ void __launch_bounds__(256) radix_split_kernel(const FwdParams p, float2 *pre, const float2 *TLM, const float2 *THM,
+                                                          int log2Mb) {
+    const size_t Mb = (size_t)1 << log2Mb;
+    const size_t nb = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const int frame = blockIdx.y;
+    const size_t half = Mb * NA / 2;
+    const char *ring = reinterpret_cast<const char *>(p.ring);
+    const void *hopA = ring + (size_t)((p.hop0 + frame) % p.nhops) * p.hop_bytes;
+    const void *hopB = ring + (size_t)((p.hop0 + frame + 1) % p.nhops) * p.hop_bytes;
+    float2 v[NA];
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        const size_t n = Mb * a + nb;
+        float2 x = (a < NA / 2) ? load_sample(hopA, p.in_format, n) : load_sample(hopB, p.in_format, n - half);
+        if constexpr (REAL) {
+            const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window) + n);
+            x.x *= w.x;
+            x.y *= w.y;
+        } else {
+            const float w = __ldg(p.window + n);
+            x.x *= w;
+            x.y *= w;
+        }
+        v[a] = x;
+    }
+    RegDft<NA>::run(v);
+    float2 *dst = pre + (size_t)frame * NA * Mb + nb;
+    dst[0] = v[0];
+#pragma unroll
+    for (int ka = 1; ka < NA; ka++) {
+        const unsigned e = (unsigned)nb * (unsigned)ka;  // < 2^23
+        dst[(size_t)ka * Mb] = cmul(v[ka], cmul(__ldg(TLM + (e & 1023u)), __ldg(THM + (e >> 10))));
     }
 }
 
@@ -277,10 +328,12 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
     extern __shared__ float2 sm[];
 
     const int tid = threadIdx.x;
-    const int frame = blockIdx.y;
+    const int na = p.na;                         // sub-transforms per frame (1 = plain)
+    const int frame = blockIdx.y / na;
+    const int ka = blockIdx.y - frame * na;
     const int N1 = p.N1, N2 = p.N2;
-    const size_t M = (size_t)1 << p.log2M;
-    const float2 *Y = p.Y + (size_t)frame * M;
+    const size_t M = (size_t)1 << p.log2M;       // sub-transform length
+    const float2 *Y = p.Y + (size_t)blockIdx.y * M;
 
     {   // stage A: lanes along n2 (contiguous in Y)
         const int r = tid % TPC;
@@ -314,10 +367,11 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
 #pragma unroll
             for (int s = 0; s < RB; s++) {
                 const unsigned u2 = q + RA * s;
-                const size_t k = ((size_t)u1 + (size_t)N1 * u2 + p.shift) & (M - 1);
+                const size_t ks = ((size_t)u1 + (size_t)N1 * u2 + p.shift) & (M - 1);
+                const size_t k = (size_t)ka + (size_t)na * ks;  // bin of the full transform
                 const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
                 out[k] = val;
-                if (k < (size_t)p.additional) out[M + k] = val;  // IQ wrap tail, src/fft.cpp:96-97
+                if (k < (size_t)p.additional) out[M * na + k] = val;  // IQ wrap tail, src/fft.cpp:96-97
                 if constexpr (FUSE == 1) pw[s] = __fadd_rn(__fmul_rn(val.x, val.x), __fmul_rn(val.y, val.y));
                 if constexpr (FUSE == 2)
                     p.pscratch[(size_t)frame * M + (size_t)u2 * N1 + u1] =
@@ -328,11 +382,12 @@ __global__ void __launch_bounds__(T *CMax<RA, RB>::v) fft_pass2_kernel(const Fwd
                     float2 *po = p.peers[pe] + (size_t)frame * p.out_stride;
 #pragma unroll
                     for (int s = 0; s < RB; s++) {
-                        const unsigned k = (unsigned)(((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1));
+                        const unsigned ks = (unsigned)(((size_t)u1 + (size_t)N1 * (q + RA * s) + p.shift) & (M - 1));
+                        const unsigned k = (unsigned)ka + (unsigned)na * ks;
                         const float2 val = make_float2(u[s].x * scale, u[s].y * scale);
                         if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1]))
                             po[k] = val;
-                        const unsigned kt = (unsigned)M + k;
+                        const unsigned kt = (unsigned)(M * na) + k;
                         if (k < (unsigned)p.additional &&
                             ((kt >= p.peer_lo[pe][0] && kt < p.peer_hi[pe][0]) || (kt >= p.peer_lo[pe][1] && kt < p.peer_hi[pe][1])))
                             po[kt] = val;

@@ -44,11 +44,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// try_wait suspends for a hardware-defined time slice per attempt; a transfer that never lands (a bug) traps after
-// ~2^22 attempts instead of hanging the GPU
+// A transfer that never lands would be a bug in this file; rather than hang the GPU, a wait that has lasted more
+// than five seconds of wall time (globaltimer, checked every 4096 failed attempts) traps.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
-        if (spins > (1u << 22)) __trap();
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 1; !mbar_try_wait(bar, parity); spins++) {
+        if ((spins & 4095u) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 5000000000ull) __trap();
+        }
+    }
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -412,8 +424,11 @@ __global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const Fwd
     const int tiles_per_frame = N1 / T;
     const int total = tiles_per_frame * nframes;
     const size_t M = (size_t)N1 * N2;
+    // One "full" barrier per (stage, consumer group): tile j completes on full[j % 3][j % 2], phase j / 6. A group only
+    // ever waits on its own barriers, one phase after the other, so a parity wait can never be satisfied by an older
+    // phase (with a barrier shared by both groups, a group running two phases ahead of a slow transfer would be).
     if (tid == 0) {
-        for (int s = 0; s < kP3Stages; s++) mbar_init(full + s, 1);
+        for (int s = 0; s < kP3Stages * kP3Groups; s++) mbar_init(full + s, 1);
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -427,10 +442,11 @@ __global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const Fwd
         const int i = blockIdx.x + j * gridDim.x;
         const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
         const int st = j % kP3Stages;
-        mbar_expect_tx(full + st, sizeof(float2) * N2 * T);
+        uint64_t *bar = full + st * kP3Groups + (j % kP3Groups);
+        mbar_expect_tx(bar, sizeof(float2) * N2 * T);
         const unsigned char *src = reinterpret_cast<const unsigned char *>(p.Y + (size_t)frame * M + (size_t)tile * T * N2);
         unsigned char *dst = smem_raw + (size_t)st * P3Smem::kStage;
-        for (int k = 0; k < 4; k++) bulk_load_1d(dst + k * 16384, src + k * 16384, 16384, full + st);
+        for (int k = 0; k < 4; k++) bulk_load_1d(dst + k * 16384, src + k * 16384, 16384, bar);
     };
     if (tid == 0)
         for (int j = 0; j < kP3Stages; j++)
@@ -441,7 +457,7 @@ __global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const Fwd
         const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
         const int st = j % kP3Stages;
         float2 *sm = reinterpret_cast<float2 *>(smem_raw + (size_t)st * P3Smem::kStage);
-        mbar_wait(full + st, (j / kP3Stages) & 1);
+        mbar_wait(full + st * kP3Groups + g, (j / (kP3Stages * kP3Groups)) & 1);
         {   // stage A: lanes along n2
             const int r = gt % 32;
             const int c = gt / 32;

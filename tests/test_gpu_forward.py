@@ -26,16 +26,14 @@ CONFIGS = [
 ]
 
 
-@pytest.mark.parametrize("cfg", CONFIGS)
-def test_forward_and_pyramid_match_oracle(gpu_required, cfg):
-    src = SignalSource(cfg, seed=0x5EED + cfg.fft_size % 97)
+def _run_frames_against_oracle(cfg, next_hop, nframes):
+    """Drive engine and oracle with the reference's ring order (src/fft.cpp:47-105) and compare every frame."""
     orc = make_oracle_fft(cfg)
     eng = make_engine(cfg)
     ring = [eng.malloc(cfg.hop_floats) for _ in range(3)]
-    ring[0][:] = hop_as_floats(src.next_hop())
-    ring[1][:] = hop_as_floats(src.next_hop())
+    ring[0][:] = hop_as_floats(next_hop())
+    ring[1][:] = hop_as_floats(next_hop())
     idx = 0
-    nframes = 3 if cfg.fft_size <= (1 << 19) else 2
     R = cfg.fft_result_size
     for frame in range(nframes):
         a1, a2 = ring[idx], ring[(idx + 1) % 3]
@@ -45,14 +43,14 @@ def test_forward_and_pyramid_match_oracle(gpu_required, cfg):
         else:
             eng.load_complex_input(a1, a2)
             orc.load_complex_input(a1, a2)
-        ring[(idx + 2) % 3][:] = hop_as_floats(src.next_hop())  # the async read of fft.cpp:56-67
+        ring[(idx + 2) % 3][:] = hop_as_floats(next_hop())  # the async read of fft.cpp:56-67
         idx = (idx + 1) % 3
         eng.execute()
         orc.execute()
         nb = R + 1 if cfg.is_real else R
         got = eng.get_output_buffer().view(np.complex64)
         ref = orc.spectrum
-        rel = spectrum_tolerance_check(got[:R], ref[:R])
+        spectrum_tolerance_check(got[:R], ref[:R])
         if cfg.is_real:
             # Nyquist bin stays unnormalised in the reference (src/fft_impl.cpp:152-154)
             assert abs(got[R] - ref[R]) <= 1e-5 * cfg.fft_size * np.abs(ref[:R]).max()
@@ -77,6 +75,49 @@ def test_forward_and_pyramid_match_oracle(gpu_required, cfg):
     for b in ring:
         eng.free(b)
     eng.close()
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_forward_and_pyramid_match_oracle(gpu_required, cfg):
+    src = SignalSource(cfg, seed=0x5EED + cfg.fft_size % 97)
+    _run_frames_against_oracle(cfg, src.next_hop, 3 if cfg.fft_size <= (1 << 19) else 2)
+
+
+LARGE = [
+    pytest.param(SpectrumConfig(sps=35_000_000, fft_size=1 << 21, is_real=False), id="iq-2^21"),
+    pytest.param(SpectrumConfig(sps=35_000_000, fft_size=1 << 22, is_real=False), id="iq-2^22"),
+    pytest.param(SpectrumConfig(sps=35_000_000, fft_size=1 << 23, is_real=False), id="iq-2^23"),
+    pytest.param(SpectrumConfig(sps=70_000_000, fft_size=1 << 22, is_real=True), id="real-2^22"),
+    pytest.param(SpectrumConfig(sps=70_000_000, fft_size=1 << 23, is_real=True), id="real-2^23"),
+]
+
+
+@pytest.mark.parametrize("cfg", LARGE)
+def test_large_transform_sizes(gpu_required, cfg):
+    """BASELINE.json configs[4] sweeps 2^16..2^23: above 2^20 complex points the engine runs a radix-2/4/8 split in
+    front of 2^20-point sub-transforms (deep pyramids: up to 14 levels, pyramid_tail_kernel). Light input (noise + a few
+    tones below the int8 wrap level) so the CPU oracle stays within seconds."""
+    rng = np.random.default_rng(0xB200 + cfg.fft_size % 1013 + int(cfg.is_real))
+    n = cfg.hop_samples
+    scale = float(np.sqrt(2.0 ** 20 / cfg.fft_size))
+    tones = [(rng.uniform(0.02, 0.48) if cfg.is_real else rng.uniform(-0.48, 0.48), rng.uniform(2e-4, 1.2e-3) * scale,
+              rng.uniform(0, 2 * np.pi)) for _ in range(3)]
+    pos = [0]
+
+    def next_hop():
+        t = np.arange(pos[0], pos[0] + n, dtype=np.float64)
+        pos[0] += n
+        if cfg.is_real:
+            x = rng.standard_normal(n) * (1e-3 * scale)
+            for f, a, ph in tones:
+                x += a * np.cos(2 * np.pi * f * t + ph)
+            return x.astype(np.float32)
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (1e-3 * scale)
+        for f, a, ph in tones:
+            x += a * np.exp(1j * (2 * np.pi * f * t + ph))
+        return x.astype(np.complex64)
+
+    _run_frames_against_oracle(cfg, next_hop, 2)
 
 
 def test_known_answer_tone_bin_and_level(gpu_required):
