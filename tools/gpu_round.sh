@@ -1,12 +1,14 @@
 #!/bin/bash
+# One round of GPU evidence for profiles/: GPU tests, the bench line, the ncu launch list of the same command and one
+# ncu --set full capture of the forward kernels. Run as: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh'
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.txt
-tail -8 gpurun_out/pytest_gpu.txt
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks.csv &
-SMI=$!
-timeout 600 python bench.py --steps 30 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-kill $SMI
+tail -4 gpurun_out/pytest_gpu.txt
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.txt 2>&1; tail -1 gpurun_out/smoke.txt
+timeout 600 python bench.py --steps 30 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 cat gpurun_out/bench.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"
+cat gpurun_out/bench_ref.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:fft_|pyramid|client_|radix' -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_ncu.log 2>&1
 python profiles/ncu_summary.py gpurun_out/launches.csv
