@@ -102,6 +102,8 @@ struct b200_engine {
     int na = 1;        // M = na * Mb: radix-na split in front of na two-pass sub-transforms (M > 2^20)
     int log2Mb = 0;    // sub-transform length (== log2M when na == 1)
     float2 *d_pre = nullptr, *d_TLM = nullptr, *d_THM = nullptr;
+    unsigned *d_done = nullptr;         // [lanes][64] tiles of each frame stored by the fused pass-2 + pyramid kernel
+    int opt_pyr_lag = 2;                // fused kernel: frames between a tile and the pyramid blocks that ride on it
     size_t R = 0;  // fft_result_size
     SubPlan sp1{}, sp2{};
     cudaStream_t stream = nullptr;      // the stream forward work is enqueued on
@@ -328,6 +330,12 @@ int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    if (!e->d_done) {
+        CU(cudaMalloc(&e->d_done, sizeof(unsigned) * 4 * 64));  // per-frame tile counters of the fused kernel, one row per lane
+        CU(cudaMemset(e->d_done, 0, sizeof(unsigned) * 4 * 64));
+    }
     e->tma_ok = true;
     return 0;
 }
@@ -352,15 +360,23 @@ int launch_tma_pass1(b200_engine *e, const FwdParams &p, int frames) {
     CU(cudaGetLastError());
     return 0;
 }
-int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse) {
+int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse, const PyrParams *pyr = nullptr, int lane = 0) {
     const int total = (kS / kTmaT) * frames;
     if (e->opt_tma >= 2 && fuse != 1) {  // three-stage variant: one CTA of two consumer groups per SM
         const int grid = std::min(total, e->num_sms);
         const bool peers = p.npeers > 0;
-        if (fuse == 2 && !peers) fft_pass2_tma3_kernel<2, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
-        else if (fuse == 2) fft_pass2_tma3_kernel<2, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
-        else if (!peers) fft_pass2_tma3_kernel<0, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
-        else fft_pass2_tma3_kernel<0, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames);
+        PyrParams none{};
+        if (pyr) {  // spectrum + whole pyramid in one launch (FUSE 3): zero the per-frame tile counters first
+            unsigned *done = e->d_done + 64 * lane;
+            CU(cudaMemsetAsync(done, 0, sizeof(unsigned) * 64, e->stream));
+            const int lag = std::max(1, e->opt_pyr_lag);
+            if (!peers) fft_pass2_tma3_kernel<3, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, *pyr, done, lag);
+            else fft_pass2_tma3_kernel<3, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, *pyr, done, lag);
+        } else if (fuse == 2 && !peers)
+            fft_pass2_tma3_kernel<2, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, none, nullptr, 0);
+        else if (fuse == 2) fft_pass2_tma3_kernel<2, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, none, nullptr, 0);
+        else if (!peers) fft_pass2_tma3_kernel<0, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, none, nullptr, 0);
+        else fft_pass2_tma3_kernel<0, true><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, none, nullptr, 0);
         e->launches++;
         CU(cudaGetLastError());
         return 0;
@@ -467,22 +483,6 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         base_level = 0;
         while ((1 << base_level) < kTmaT) base_level++;
     }
-    if (e->na > 1) {
-        if (e->opt_stage_mask & 1) {
-            rc = launch_split(e, p, frames);
-            if (!rc) rc = launch_pass1r<32, 32, 16, false, true, true>(e, p, frames * e->na);
-        }
-        if (rc) return rc;
-        if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames * e->na, 0);
-        if (rc) return rc;
-    } else {
-        if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
-        if (rc) return rc;
-        if (e->opt_stage_mask & 2) rc = tma ? launch_tma_pass2(e, p, frames, fuse) : dispatch_pass2(e, p, frames, fuse);
-        if (rc) return rc;
-    }
-    if (!(e->opt_stage_mask & 4)) return 0;
-
     PyrParams q{};
     q.spec = spec;
     q.spec_stride = e->spec_stride;
@@ -504,6 +504,33 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     q.N2 = e->sp2.S;
     q.npeers = e->is_real ? e->npeers : 0;
     for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i] + (size_t)f0 * e->spec_stride;
+    // opt_tma 3: pass 2 of the TMA path also produces the whole pyramid (FUSE 3), unless a stage is masked out for profiling
+    const bool fused = tma && e->opt_tma >= 3 && fuse == 0 && !e->is_real && e->na == 1 && (e->opt_packed & 1) &&
+                       (e->opt_stage_mask & 6) == 6 && frames <= 64 && e->levels > 0 &&
+                       e->opt_lanes <= 1;  // its CTAs wait on one another: never two such grids competing for the SMs
+    if (e->na > 1) {
+        if (e->opt_stage_mask & 1) {
+            rc = launch_split(e, p, frames);
+            if (!rc) rc = launch_pass1r<32, 32, 16, false, true, true>(e, p, frames * e->na);
+        }
+        if (rc) return rc;
+        if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames * e->na, 0);
+        if (rc) return rc;
+    } else {
+        if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
+        if (rc) return rc;
+        if (e->opt_stage_mask & 2) rc = tma ? launch_tma_pass2(e, p, frames, fuse, fused ? &q : nullptr, lane) : dispatch_pass2(e, p, frames, fuse);
+        if (rc) return rc;
+    }
+    if (!(e->opt_stage_mask & 4)) return 0;
+    if (fused) {  // only very deep pyramids have levels left (sums in ptop)
+        if (e->levels > 13) {
+            pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q, 0, 13);
+            e->launches++;
+            CU(cudaGetLastError());
+        }
+        return 0;
+    }
     if (e->levels > q.base_level) {
         // 16 entries per thread for the full-resolution inputs, 4 for the small per-tile sums of mode 1
         const int per = (fuse == 1) ? 4 : 16;
@@ -1040,6 +1067,10 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_PEER_STORES: e->opt_peer_stores = value ? 1 : 0; return 0;
     case B200_OPT_TAIL_PIPELINE: e->opt_tail_pipe = value ? 1 : 0; return 0;
     case B200_OPT_PACKED_MATH: e->opt_packed = value & 1; return 0;
+    case B200_OPT_PYRAMID_LAG:
+        if (value < 1 || value > 8) return fail(B200_EINVAL, "pyramid lag must be 1..8 frames");
+        e->opt_pyr_lag = value;
+        return 0;
     case B200_OPT_PASS1_ORDER:
         if (value < 0 || value > 2) return fail(B200_EINVAL, "pass-1 order must be 0, 1 or 2");
         e->opt_pass1_order = value;

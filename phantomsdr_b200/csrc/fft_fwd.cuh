@@ -477,15 +477,20 @@ struct PyrParams {
 // grid ((R >> base_level) / (256*PER), frames), block 256: each thread owns PER (4 or 16) consecutive entries of the
 // base level; the block then reduces log2(PER) levels in registers, five with warp shuffles and three through
 // shared memory (pairwise sums, src/fft_impl.cpp:45-61,162-172) - log2(PER) + 8 levels above the base in all.
-template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+struct CtaSync {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// One block of 256 threads (a CTA of pyramid_kernel, or one consumer group of the fused FFT kernel): `blk` = block
+// index within the frame, `tid` = 0..255, `warp_sum_s` = 8 floats of shared memory, `sync` = barrier of those 256
+// threads. CG: spectrum loads bypass L1 (the fused kernel reads bins that other SMs stored during the same launch).
+template <int MODE, int PER, bool PK, bool CG, typename Sync>
+__device__ __forceinline__ void pyramid_block(const PyrParams &p, const int frame, const unsigned blk, const int tid,
+                                              float *warp_sum_s, Sync sync) {
     static_assert(PER == 4 || PER == 16, "PER must be 4 or 16");
     constexpr int LP = (PER == 16) ? 4 : 2;  // levels reduced in registers
-    __shared__ float warp_sum_s[8];
-    const int tid = threadIdx.x;
-    const int frame = blockIdx.y;
     const unsigned R = 1u << p.log2R;  // bins and pyramid offsets fit 32 bits (R <= 2^23)
     const int B = (MODE == PYR_SCRATCH) ? p.base_level : 0;
-    const unsigned d0 = (blockIdx.x * 256u + tid) * PER;  // index at level B
+    const unsigned d0 = (blk * 256u + tid) * PER;  // index at level B
     int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
 
     float pw[PER];
@@ -500,7 +505,7 @@ template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyr
             const float4 *src = reinterpret_cast<const float4 *>(spec + k0);
 #pragma unroll
             for (int i = 0; i < PER / 2; i++) {
-                const float4 x = src[i];
+                const float4 x = CG ? __ldcg(src + i) : src[i];
                 if constexpr (PK) {  // (re^2, im^2) in one FMUL2, then the separately rounded sum
                     float a, b, c, d;
                     const unsigned long long v0 = pk(x.x, x.y), v1 = pk(x.z, x.w);
@@ -516,7 +521,8 @@ template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyr
         } else {
 #pragma unroll
             for (int i = 0; i < PER; i++) {
-                const float2 x = spec[(k0 + i) & (R - 1)];
+                const float2 *src = spec + ((k0 + i) & (R - 1));
+                const float2 x = CG ? __ldcg(src) : *src;
                 pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
             }
         }
@@ -606,10 +612,10 @@ template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyr
         }
         if (L > LP + 6) {
             if (lane == 0) warp_sum_s[tid >> 5] = s;
-            __syncthreads();
+            sync();
             if (tid < 8) {
                 float w = warp_sum_s[tid];
-                const unsigned b0 = blockIdx.x * 256u * PER;
+                const unsigned b0 = blk * 256u * PER;
 #pragma unroll
                 for (int k = 1; k <= 3; k++) {  // relative levels LP+6 .. LP+8 across the eight warps
                     const int lv = LP + 5 + k;
@@ -620,10 +626,15 @@ template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyr
                         lvl_off += RB_ >> lv;
                     }
                 }
-                if (L > LP + 9 && tid == 0) p.ptop[(size_t)frame * (RB_ / (256 * PER)) + blockIdx.x] = w;
+                if (L > LP + 9 && tid == 0) p.ptop[(size_t)frame * (RB_ / (256 * PER)) + blk] = w;
             }
         }
     }
+}
+
+template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+    __shared__ float warp_sum_s[8];
+    pyramid_block<MODE, PER, PK, false>(p, blockIdx.y, blockIdx.x, threadIdx.x, warp_sum_s, CtaSync{});
 }
 
 // more than ten levels above the base (only for very deep pyramids): one block per frame, pairwise tree over

@@ -400,7 +400,7 @@ constexpr int kP3Stages = 3;
 struct P3Smem {
     static constexpr size_t kStage = sizeof(float2) * 32 * TmaSmem::kRow2;   // 65 792 B: raw tile (64 KiB) or exchange
     static constexpr size_t kTw = sizeof(float2) * 32 * 32;
-    static constexpr size_t kTotal = kP3Stages * kStage + kTw + 64;
+    static constexpr size_t kTotal = kP3Stages * kStage + kTw + 64 + 64;  // + mbarriers + 2 x 8 warp sums (fused pyramid)
 };
 static_assert(P3Smem::kStage % 16 == 0, "stage must stay 16-byte aligned for bulk copies");
 static_assert(P3Smem::kTotal <= 232448, "exceeds the 227 KiB per-CTA shared memory limit");
@@ -409,14 +409,41 @@ __device__ __forceinline__ void group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kTmaThreads) : "memory");
 }
 
+struct GroupSync {
+    int g;
+    __device__ __forceinline__ void operator()() const { group_sync(g); }
+};
+// spin until *counter >= target (acquire); a counter that never gets there is a bug: trap after five seconds
+__device__ __forceinline__ void wait_counter(const unsigned *counter, unsigned target) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 1;; spins++) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) return;
+        __nanosleep(100);
+        if ((spins & 1023u) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 5000000000ull) __trap();
+        }
+    }
+}
+
+// FUSE: 0 = spectrum only, 2 = + |X|^2 plane, 3 = spectrum + the whole waterfall pyramid inside this kernel: after a
+// tile of frame f a group quantises two 4096-bin blocks of frame f - lag, whose bins every CTA has stored by then
+// (per-frame completion counters `done`, release/acquire at GPU scope) and which are still in L2 - no second kernel,
+// no re-read of the spectrum from DRAM. All CTAs are co-resident (grid <= SMs, one CTA per SM) and every wait targets
+// work that precedes the waiter in the common tile order, so the waits cannot deadlock.
 template <int FUSE, bool PEERS>
-__global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const FwdParams p, int nframes) {
+__global__ void __launch_bounds__(kP3Threads, 1)
+    fft_pass2_tma3_kernel(const FwdParams p, int nframes, const PyrParams pyr, unsigned *done, int lag) {
     constexpr int T = kTmaT, RA = 32, RB = 32, N1 = kS, N2 = kS;
     constexpr int ROW = TmaSmem::kRow2;
-    static_assert(FUSE == 0 || FUSE == 2, "the three-stage kernel has no room for the in-kernel waterfall epilogue");
+    static_assert(FUSE == 0 || FUSE == 2 || FUSE == 3, "the three-stage kernel has no room for the smem-tiled waterfall epilogue");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float2 *twA = reinterpret_cast<float2 *>(smem_raw + kP3Stages * P3Smem::kStage);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + kP3Stages * P3Smem::kStage + P3Smem::kTw);
+    float *wsum = reinterpret_cast<float *>(smem_raw + kP3Stages * P3Smem::kStage + P3Smem::kTw + 64);
 
     const int tid = threadIdx.x;
     const int g = tid / kTmaThreads;       // consumer group
@@ -452,6 +479,14 @@ __global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const Fwd
         for (int j = 0; j < kP3Stages; j++)
             if ((int)blockIdx.x + j * (int)gridDim.x < total) issue_tile(j);
 
+    auto pyramid_blocks = [&](int fp, int blk0, int count) {
+        if (gt == 0) wait_counter(done + fp, (unsigned)tiles_per_frame);  // every bin of frame fp is stored and visible
+        group_sync(g);
+        for (int b = 0; b < count; b++) {
+            pyramid_block<PYR_SPEC, 16, true, true>(pyr, fp, (unsigned)(blk0 + b), gt, wsum + 8 * g, GroupSync{g});
+            group_sync(g);  // the block's warp sums are consumed before the next block overwrites them
+        }
+    };
     for (int j = g; (int)blockIdx.x + j * (int)gridDim.x < total; j += kP3Groups) {
         const int i = blockIdx.x + j * gridDim.x;
         const int frame = i / tiles_per_frame, tile = i - frame * tiles_per_frame;
@@ -467,7 +502,6 @@ __global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const Fwd
             group_sync(g);
             RegDft<RA>::run(v);
             const float2 *tw = twA + r;
-#pragma unroll
             sm[r * ROW + c] = make_float2(v[0].x * scale, v[0].y * scale);
 #pragma unroll
             for (int qq = 1; qq < RA; qq++) sm[r * ROW + qq * T + c] = cmul(v[qq], tw[qq * RB]);
@@ -524,6 +558,22 @@ __global__ void __launch_bounds__(kP3Threads, 1) fft_pass2_tma3_kernel(const Fwd
                 }
             }
         }
+        if constexpr (FUSE == 3) {
+            // publish this tile (every thread fences its own stores, then one arrival per tile) ...
+            __threadfence();
+            group_sync(g);
+            if (gt == 0) atomicAdd(done + frame, 1u);
+            // ... and quantise the two pyramid blocks that pair with it, `lag` frames back
+            if (frame >= lag) pyramid_blocks(frame - lag, 2 * tile, 2);
+        }
+    }
+    if constexpr (FUSE == 3) {
+        // the last `lag` frames have no later tile to ride on: their blocks are spread over all groups
+        constexpr int kBlocksPerFrame = N1 * N2 / (256 * 16);
+        const int first = nframes > lag ? nframes - lag : 0;
+        const int nblocks = (nframes - first) * kBlocksPerFrame;
+        for (int b = (int)blockIdx.x * kP3Groups + g; b < nblocks; b += kP3Groups * (int)gridDim.x)
+            pyramid_blocks(first + b / kBlocksPerFrame, b % kBlocksPerFrame, 1);
     }
 }
 

@@ -40,7 +40,7 @@ def test_forward_variants_bit_identical(gpu_required):
     F = 8
     eng, torch, B = _device_engine(cfg, F, 12)
     defaults = {B.OPT_FUSED_PYRAMID: -1, B.OPT_TMA: 2, B.OPT_PACKED_MATH: 1, B.OPT_FWD_LANES: 1, B.OPT_FWD_SUB_FRAMES: 64,
-                B.OPT_PASS1_ORDER: 0}
+                B.OPT_PASS1_ORDER: 0, B.OPT_PYRAMID_LAG: 2}
     variants = [
         {},
         {B.OPT_PACKED_MATH: 0},
@@ -53,6 +53,11 @@ def test_forward_variants_bit_identical(gpu_required):
         {B.OPT_FWD_SUB_FRAMES: 2},
         {B.OPT_FWD_LANES: 2, B.OPT_FWD_SUB_FRAMES: 2},
         {B.OPT_FWD_LANES: 4, B.OPT_FWD_SUB_FRAMES: 1},
+        {B.OPT_TMA: 3},                                # pyramid fused into pass 2 (per-frame completion counters)
+        {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 1},
+        {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 3},
+        {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 8},          # lag >= frames: every block is produced by the tail loop
+        {B.OPT_TMA: 3, B.OPT_FWD_LANES: 2, B.OPT_FWD_SUB_FRAMES: 2},
     ]
     ref = None
     for opts in variants:

@@ -5,7 +5,7 @@ sys.path.insert(0, '.')
 import torch
 from phantomsdr_b200 import SpectrumConfig
 from phantomsdr_b200.backend import (B200FFT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_PACKED_MATH, OPT_FWD_LANES,
-                                     OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER)
+                                     OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER, OPT_PYRAMID_LAG)
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 H = 64
@@ -22,7 +22,7 @@ ring = torch.as_tensor(eng.device_hop_ring(H), device='cuda')
 ring.normal_(0, 1e-3)
 torch.cuda.synchronize()
 
-DEFAULTS = {OPT_FUSED_PYRAMID: 2, OPT_TMA: 1, OPT_PACKED_MATH: 1, OPT_FWD_LANES: 1, OPT_FWD_SUB_FRAMES: 64, OPT_PASS1_ORDER: 0}
+DEFAULTS = {OPT_FUSED_PYRAMID: -1, OPT_PYRAMID_LAG: 2, OPT_TMA: 2, OPT_PACKED_MATH: 1, OPT_FWD_LANES: 1, OPT_FWD_SUB_FRAMES: 64, OPT_PASS1_ORDER: 0}
 
 
 def configure(opts):
@@ -55,22 +55,11 @@ def t(mask, reps=10):
 
 
 VARIANTS = [
-    ("base tma1 scalar-q", {OPT_PACKED_MATH: 0}),
-    ("tma1 packed-q", {}),
-    ("tma2 (3-stage p2)", {OPT_TMA: 2}),
-    ("tma2 order1", {OPT_TMA: 2, OPT_PASS1_ORDER: 1}),
-    ("tma2 order2", {OPT_TMA: 2, OPT_PASS1_ORDER: 2}),
-    ("tma2 fuse0", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0}),
-    ("tma2 fuse0 scalar-q", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_PACKED_MATH: 0}),
-    ("tma2 f2 L2 s4", {OPT_TMA: 2, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
-    ("tma2 f0 L2 s4", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
-    ("tma2 f0 L2 s2", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 2}),
-    ("tma2 f0 L3 s2", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 3, OPT_FWD_SUB_FRAMES: 2}),
-    ("tma2 f0 L3 s4", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 3, OPT_FWD_SUB_FRAMES: 4}),
-    ("tma2 f0 L4 s4", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 4, OPT_FWD_SUB_FRAMES: 4}),
-    ("tma2 f0 L2 s8", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 8}),
-    ("tma2 f0 L2 s4 o2", {OPT_TMA: 2, OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4, OPT_PASS1_ORDER: 2}),
-    ("tma1 f0 L2 s4", {OPT_FUSED_PYRAMID: 0, OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
+    ("tma2 fuse0 (default)", {OPT_TMA: 2}),
+    ("tma3 lag1", {OPT_TMA: 3, OPT_PYRAMID_LAG: 1}),
+    ("tma3 lag2", {OPT_TMA: 3, OPT_PYRAMID_LAG: 2}),
+    ("tma3 lag3", {OPT_TMA: 3, OPT_PYRAMID_LAG: 3}),
+    ("tma3 lag4", {OPT_TMA: 3, OPT_PYRAMID_LAG: 4}),
 ]
 ref = None
 for name, opts in VARIANTS:
@@ -85,7 +74,7 @@ for name, opts in VARIANTS:
         ds = (spec - ref[0]).abs().max().item()
         nq = (quant != ref[1]).sum().item()
         chk = f"spec maxdiff {ds:.3e} (max {ref[0].abs().max().item():.3e})  pyramid bytes differing {nq}"
-    full = len(opts) == 0 or OPT_FWD_LANES not in opts and OPT_FWD_SUB_FRAMES not in opts
+    full = opts.get(OPT_TMA, 2) != 3
     if full:
         print(f"{name:20s} batch {F}: pass1 {t(1):.2f}  pass2 {t(2):.2f}  pyramid {t(4):.2f}  all {t(7):.2f} us/frame | {chk}", flush=True)
     else:
