@@ -1,9 +1,11 @@
-"""Times the forward stages alone (HBM-resident ring) for a few engine options. Usage: python tools/fwdprobe.py [batch]"""
-import sys, json
+"""Forward-group variants: bit-for-bit comparison against the first variant, then per-stage timings (edit VARIANTS).
+Usage: python tools/fwdprobe.py [batch]"""
+import sys
 sys.path.insert(0, '.')
 import torch
 from phantomsdr_b200 import SpectrumConfig
-from phantomsdr_b200.backend import B200FFT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA
+from phantomsdr_b200.backend import (B200FFT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_PACKED_MATH, OPT_FWD_LANES,
+                                     OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER, OPT_PYRAMID_LAG)
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 H = 64
@@ -18,6 +20,22 @@ torch.cuda.set_stream(s)
 eng.set_stream(s.cuda_stream)
 ring = torch.as_tensor(eng.device_hop_ring(H), device='cuda')
 ring.normal_(0, 1e-3)
+torch.cuda.synchronize()
+
+DEFAULTS = {OPT_FUSED_PYRAMID: -1, OPT_PYRAMID_LAG: 2, OPT_TMA: 2, OPT_PACKED_MATH: 1, OPT_FWD_LANES: 1, OPT_FWD_SUB_FRAMES: 64, OPT_PASS1_ORDER: 0}
+
+
+def configure(opts):
+    for k, v in {**DEFAULTS, **opts}.items():
+        eng.set_option(k, v)
+
+
+def snapshot():
+    eng.execute_device(3, F)
+    torch.cuda.synchronize()
+    spec = torch.as_tensor(eng.device_spectrum(F), device='cuda').clone()
+    quant = torch.as_tensor(eng.device_quantized(F), device='cuda').clone()
+    return spec, quant
 
 
 def t(mask, reps=10):
@@ -36,10 +54,33 @@ def t(mask, reps=10):
     return a.elapsed_time(b) * 1e3 / (reps * H)
 
 
-for name, opts in (("tma power(2)", {}), ("tma fused(1)", {OPT_FUSED_PYRAMID: 1}), ("tma unfused(0)", {OPT_FUSED_PYRAMID: 0}),
-                   ("no tma power", {OPT_TMA: 0})):
-    eng.set_option(OPT_FUSED_PYRAMID, 2)
-    eng.set_option(OPT_TMA, 1)
-    for k, v in opts.items():
-        eng.set_option(k, v)
-    print(f"{name:14s} batch {F}: pass1 {t(1):.2f}  pass2 {t(2):.2f}  pyramid {t(4):.2f}  all {t(7):.2f} us/frame")
+VARIANTS = [
+    ("default (tma2 fuse0)", {}),
+    ("scalar quantiser", {OPT_PACKED_MATH: 0}),
+    ("tma1 two-CTA pass 2", {OPT_TMA: 1}),
+    ("power plane (fuse 2)", {OPT_FUSED_PYRAMID: 2}),
+    ("pass-1 order 1", {OPT_PASS1_ORDER: 1}),
+    ("pass-1 order 2", {OPT_PASS1_ORDER: 2}),
+    ("2 lanes x 4 frames", {OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
+    ("sub-batches of 8", {OPT_FWD_SUB_FRAMES: 8}),
+    ("tma3 fused lag1", {OPT_TMA: 3, OPT_PYRAMID_LAG: 1}),
+    ("tma3 fused lag2", {OPT_TMA: 3, OPT_PYRAMID_LAG: 2}),
+]
+ref = None
+for name, opts in VARIANTS:
+    if F < 16 and opts.get(OPT_FWD_SUB_FRAMES, 64) * opts.get(OPT_FWD_LANES, 1) > F:
+        continue
+    configure(opts)
+    spec, quant = snapshot()
+    if ref is None:
+        ref = (spec, quant)
+        chk = "reference"
+    else:
+        ds = (spec - ref[0]).abs().max().item()
+        nq = (quant != ref[1]).sum().item()
+        chk = f"spec maxdiff {ds:.3e} (max {ref[0].abs().max().item():.3e})  pyramid bytes differing {nq}"
+    full = opts.get(OPT_TMA, 2) != 3 and OPT_FWD_LANES not in opts and OPT_FWD_SUB_FRAMES not in opts
+    if full:
+        print(f"{name:20s} batch {F}: pass1 {t(1):.2f}  pass2 {t(2):.2f}  pyramid {t(4):.2f}  all {t(7):.2f} us/frame | {chk}", flush=True)
+    else:
+        print(f"{name:20s} batch {F}: all {t(7):.2f} us/frame | {chk}", flush=True)
