@@ -58,6 +58,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-frames", type=int, default=768)
+    ap.add_argument("--e2e-raw", default="", choices=["", "s16", "u8"],
+                    help="also time the e2e path with raw ADC samples handed to b200_load_raw_input's block form (SURVEY 8f N1: "
+                         "sample conversion fused into FFT pass 1, 2x / 4x fewer H2D bytes); reported as e2e_raw, never as e2e")
     ap.add_argument("--mgpu-mode", default="scatter-dma", choices=["spectrum", "scatter", "scatter-dma"],
                     help="N>1 exchange step. spectrum: NCCL broadcast of every spectrum batch (north_star's wording). scatter: "
                          "clients partitioned in (l, r) order and FFT pass 2 on the ingest rank stores each rank's sub-band "
@@ -584,6 +587,55 @@ def run_b200(args):
                        "(H2D of every new half) -> forward FFT + pyramid -> clients -> D2H of the int8 pyramid and "
                        "PCM/pwr/valid of every frame; two blocks in flight; every rank drives its own host path"}
 
+    e2e_raw = None
+    if e2e is not None and args.e2e_raw and not cfg.is_real:
+        try:
+            from phantomsdr_b200.backend import OPT_INPUT_FORMAT, _FMT_OF_DTYPE
+            dt = np.int16 if args.e2e_raw == "s16" else np.uint8
+            eng.join_streams()
+            eng.sync()
+            eng.set_option(OPT_INPUT_FORMAT, _FMT_OF_DTYPE[np.dtype(dt).name])
+            rawsets = []
+            for _ in range(2):
+                halves = []
+                for _k in range(F):
+                    hb = eng.pinned(cfg.hop_floats * np.dtype(dt).itemsize, dt)
+                    if dt == np.int16:
+                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 33.0).astype(np.int16)       # ~1e-3 full scale
+                    else:
+                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 2.0 + 128.0).astype(np.uint8)
+                    halves.append(hb)
+                rawsets.append(halves)
+            prime_raw = eng.pinned(cfg.hop_floats * np.dtype(dt).itemsize, dt)
+            prime_raw[:] = rawsets[0][0]
+
+            def raw_run(blocks, f0):
+                eng.stream_prime(prime_raw)
+                for k in range(blocks):
+                    st = sets[k & 1]
+                    if k >= 2:
+                        eng.wait_block()
+                    eng.submit_block(rawsets[k & 1], f0 + k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
+                for _ in range(min(2, blocks)):
+                    eng.wait_block()
+
+            raw_run(3, 0)
+            barrier()
+            t0 = time.perf_counter()
+            raw_run(nblk, 3 * F)
+            dtm = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dtm], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtm = float(t.item())
+            e2e_raw = {"value": world * nblk * F * cfg.hop_samples / dtm / 1e6, "unit": UNIT, "format": args.e2e_raw,
+                       "h2d_bytes_per_step": cfg.hop_floats * np.dtype(dt).itemsize * H, "d2h_bytes_per_step": dbytes * H,
+                       "frames_timed": nblk * F,
+                       "path": "as e2e, but the halves are raw ADC samples and SampleConverter (src/samplereader.cpp:29-66) runs "
+                               "inside FFT pass 1 (generic pass kernels)"}
+        except Exception as exc:
+            e2e_raw = {"value": None, "unit": UNIT, "format": args.e2e_raw, "error": repr(exc)}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -605,6 +657,7 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "breakdown": breakdown,
+            **({"e2e_raw": e2e_raw} if e2e_raw is not None else {}),
             "ingest_msps": ingest,
             "realtime_margin": ingest / (cfg.sps / 1e6),
         }

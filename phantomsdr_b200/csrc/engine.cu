@@ -953,7 +953,7 @@ void b200_engine_destroy(b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
-                   e->d_TLr, e->d_THr, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
+                   e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
                    e->ca.pwr, e->ca.pcm, e->ca.valid};
@@ -978,6 +978,14 @@ void b200_engine_destroy(b200_engine *e) {
         }
         cudaStreamDestroy(e->copy_stream);
     }
+    for (int l = 0; l < 4; l++) {
+        if (e->lane_stream[l]) {
+            cudaStreamSynchronize(e->lane_stream[l]);
+            cudaStreamDestroy(e->lane_stream[l]);
+        }
+        if (e->ev_lane[l]) cudaEventDestroy(e->ev_lane[l]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
