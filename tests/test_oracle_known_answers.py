@@ -40,6 +40,42 @@ def test_forward_fft_vs_numpy_and_shadow():
     assert np.abs(f.shadow_f64()[:N] - want).max() <= 1e-12 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("log2n,is_real", [(21, False), (22, True)])
+def test_large_transforms_vs_numpy(log2n, is_real):
+    """The GPU suite checks 2^21..2^23-point transforms against this oracle (tests/test_gpu_forward.py::
+    test_large_transform_sizes): pin the oracle itself at those lengths, deep pyramid included (12+ levels)."""
+    N = 1 << log2n
+    R = N // 2 if is_real else N
+    rng = np.random.default_rng(log2n)
+    L = oracle.downsample_levels(R, 1024)
+    f = oracle.OracleFFT(N, L, 0)
+    f.set_output_additional_size(0 if is_real else 720)
+    nfl = N // 2 if is_real else N
+    a1 = (rng.standard_normal(nfl) * 1e-3).astype(f32)
+    a2 = (rng.standard_normal(nfl) * 1e-3).astype(f32)
+    if is_real:
+        f.plan_r2c()
+        f.load_real_input(a1, a2)
+        x = np.concatenate([a1, a2]).astype(np.float64) * f.window
+        want = np.fft.rfft(x)[:R] / N
+    else:
+        f.plan_c2c()
+        f.load_complex_input(a1, a2)
+        x = np.concatenate([a1.view(np.complex64), a2.view(np.complex64)]).astype(np.complex128) * f.window
+        want = np.fft.fft(x) / N
+    f.execute()
+    assert np.abs(f.spectrum[:R] - want).max() <= 3e-6 * np.abs(want).max()
+    q = f.quantized
+    assert q.size == sum(R >> i for i in range(L)) and L >= 12
+    # the last level is the pairwise-sum tree all the way down: its power sums are the block sums of |X|^2
+    top = R >> (L - 1)
+    disp = np.roll(np.abs(f.spectrum[:R]) ** 2, -(R // 2 + 1)) if not is_real else np.abs(f.spectrum[:R]) ** 2
+    blocks = disp.reshape(top, -1).sum(axis=1)
+    expect = 127 + 20 * np.log10(blocks) + 6.020599913 * (log2n - (L - 1))
+    got = q[-top:].astype(np.int64)
+    assert np.abs(got - expect).max() <= 1.5  # polynomial log2 (0.05 dB) + truncation
+
+
 def test_r2c_vs_numpy_and_nyquist_left_unnormalised():
     N = 1 << 13
     rng = np.random.default_rng(1)
