@@ -122,7 +122,8 @@ int b200_execute(b200_engine *e);
                                    completion counters; experimental), 1 = two-CTA pass 2, 0 = generic kernels */
 #define B200_OPT_TAIL_PIPELINE 7 /* 1 (default): frame-skewed software pipeline for the DC/AGC tails when >= 4 frames per call */
 #define B200_OPT_PEER_STORES 8   /* 1 (default): FFT pass 2 stores the peers' sub-bands itself; 0: leave it to b200_push_peers */
-#define B200_OPT_PACKED_MATH 9   /* bit0 (default 1): waterfall quantiser on the packed-f32 pipe (FMUL2/FADD2), same IEEE rounding per lane */
+#define B200_OPT_PACKED_MATH 9   /* bit0 (default 1): waterfall quantiser on the packed-f32 pipe (FMUL2/FADD2), same IEEE rounding per lane;
+                                   bit1 (default 0, not yet validated on a GPU): table-driven quantiser for levels 0..2 (b200_quant_table) */
 #define B200_OPT_FWD_LANES 10    /* 1..4 streams that the sub-batches of one device batch alternate over (default 1) */
 #define B200_OPT_FWD_SUB_FRAMES 11 /* frames per forward launch group inside a device batch (default: the whole batch) */
 #define B200_OPT_PASS1_ORDER 12  /* tuning: work-item order of the TMA pass 1 (0 default: column tile sticky, frames swept together) */
@@ -282,6 +283,11 @@ int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const 
 
 /* Kernel-launch counter since creation (for bench.py's gpu_launches). */
 uint64_t b200_launch_count(b200_engine *e);
+/* Host-only (no GPU needed): the 2048-cell table of the table-driven waterfall quantiser for one power offset
+ * (vec_log2 + power_and_quantize, src/fft_impl.cpp:14-44, as a step function of float_bits(power) >> 20): the int8
+ * value is base[c] below lo[c], base[c] + 1 (mod 256) from hi[c] on, and needs the exact arithmetic inside [lo[c], hi[c]).
+ * Arrays of 2048 entries each. Used by B200_OPT_PACKED_MATH bit 1 and by the CPU tests. */
+int b200_quant_table(int power_offset, uint32_t *lo, uint32_t *hi, uint8_t *base);
 /* Profiling aid: accumulate the SM-clock cycles block 0 of the client tail kernel spends in each of its
  * seven phases (load, sum1, avg, sum2, peak, gain, store). out (nullable) receives the totals so far. */
 int b200_debug_tail_profile(b200_engine *e, int enable, long long out[8]);

@@ -350,3 +350,12 @@ class B200FFT:
             self.close()
         except Exception:
             pass
+
+
+def quant_table(power_offset: int):
+    """(lo, hi, base) of the table-driven waterfall quantiser for one power offset (host-only, b200_quant_table)."""
+    lo = np.zeros(2048, np.uint32)
+    hi = np.zeros(2048, np.uint32)
+    base = np.zeros(2048, np.uint8)
+    check(_ffi.lib().b200_quant_table(int(power_offset), lo.ctypes.data, hi.ctypes.data, base.ctypes.data))
+    return lo, hi, base

@@ -89,6 +89,52 @@ std::vector<float2> tw_pow(size_t count, size_t mult, size_t N) {  // [j] = exp(
 
 extern "C" int b200_set_option(struct b200_engine *e, int option, int value);
 
+// ---- table-driven waterfall quantiser (see quantize_table in fft_fwd.cuh) ----------------------------------------
+// op-for-op the reference arithmetic (src/fft_impl.cpp:14-44); the attribute keeps the host compiler from contracting
+__attribute__((optimize("-ffp-contract=off"))) static int quant_exact_host(uint32_t bits, int off) {
+    volatile float log_val = (float)((int)((bits >> 23) & 0xFF) - 128) + (float)off;
+    uint32_t mb = (bits & ~(255u << 23)) + (127u << 23);
+    float m;
+    memcpy(&m, &mb, 4);
+    volatile float t = -0.34484843f * m;
+    t = t + 2.02466578f;
+    t = t * m;
+    t = t - 0.67487759f;
+    volatile float v = log_val + t;
+    v = v * 0.3010299956639812f;
+    v = v * 20.f;
+    v = v + 127.f;
+    float vv = v;
+    vv = vv > -128.f ? vv : -128.f;
+    return (int)vv & 0xFF;
+}
+// 2048 cells indexed by bits >> 20: x = lo, y = base | (hi - lo) << 8
+static void build_quant_table(int off, uint32_t *lo_out, uint32_t *hi_out, uint8_t *base_out) {
+    const uint32_t scan = 64;  // the bands are <= 3 ulps wide (tools/quant_table.c); the bisection lands inside or next to them
+    for (uint32_t c = 0; c < 2048; c++) {
+        const uint32_t b0 = c << 20, b1 = b0 + (1u << 20);
+        const int q0 = quant_exact_host(b0, off);
+        uint32_t a = b0, b = b1;  // invariant: Q(a) == q0; b == b1 or Q(b) != q0
+        if (quant_exact_host(b1 - 1, off) == q0) a = b1 - 1;
+        while (b - a > 1) {
+            const uint32_t mid = a + (b - a) / 2;
+            if (quant_exact_host(mid, off) == q0) a = mid;
+            else b = mid;
+        }
+        uint32_t lo = b, hi = b;
+        const uint32_t s0 = b > b0 + scan ? b - scan : b0, s1 = b + scan < b1 ? b + scan : b1;
+        for (uint32_t x = s0; x < s1; x++) {
+            const bool same = quant_exact_host(x, off) == q0;
+            if (!same && x < lo) lo = x;
+            if (same && x + 1 > hi) hi = x + 1;
+        }
+        if (lo > hi) lo = hi;
+        lo_out[c] = lo;
+        hi_out[c] = hi;
+        base_out[c] = (uint8_t)q0;
+    }
+}
+
 struct b200_engine {
     int device = 0;
     size_t size = 0;
@@ -102,6 +148,7 @@ struct b200_engine {
     int na = 1;        // M = na * Mb: radix-na split in front of na two-pass sub-transforms (M > 2^20)
     int log2Mb = 0;    // sub-transform length (== log2M when na == 1)
     float2 *d_pre = nullptr, *d_TLM = nullptr, *d_THM = nullptr;
+    uint2 *d_qtab = nullptr;            // [3][2048] quantiser tables of levels 0..2 (opt_packed bit 1)
     unsigned *d_done = nullptr;         // [lanes][64] tiles of each frame stored by the fused pass-2 + pyramid kernel
     int opt_pyr_lag = 2;                // fused kernel: frames between a tile and the pyramid blocks that ride on it
     size_t R = 0;  // fft_result_size
@@ -503,6 +550,7 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     q.ntiles = fuse == 2 ? e->sp1.S : (tma ? kS / kTmaT : e->sp1.S / e->sp2.T);
     q.N2 = e->sp2.S;
     q.npeers = e->is_real ? e->npeers : 0;
+    q.qtab = (e->opt_packed & 2) ? e->d_qtab : nullptr;
     for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i] + (size_t)f0 * e->spec_stride;
     // opt_tma 3: pass 2 of the TMA path also produces the whole pyramid (FUSE 3), unless a stage is masked out for profiling
     const bool fused = tma && e->opt_tma >= 3 && fuse == 0 && !e->is_real && e->na == 1 && (e->opt_packed & 1) &&
@@ -953,7 +1001,7 @@ void b200_engine_destroy(b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
-                   e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
+                   e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_qtab, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
                    e->ca.pwr, e->ca.pcm, e->ca.valid};
@@ -1074,7 +1122,22 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_TMA: e->opt_tma = value < 0 ? 0 : (value > 3 ? 3 : value); return 0;
     case B200_OPT_PEER_STORES: e->opt_peer_stores = value ? 1 : 0; return 0;
     case B200_OPT_TAIL_PIPELINE: e->opt_tail_pipe = value ? 1 : 0; return 0;
-    case B200_OPT_PACKED_MATH: e->opt_packed = value & 1; return 0;
+    case B200_OPT_PACKED_MATH:
+        e->opt_packed = value & 3;
+        if ((value & 2) && !e->d_qtab) {  // build and upload the tables of levels 0..2
+            if (!e->planned) return fail(B200_ESTATE, "the quantiser tables need a planned engine");
+            CU(cudaSetDevice(e->device));
+            std::vector<uint2> tab(3 * 2048);
+            std::vector<uint32_t> lo(2048), hi(2048);
+            std::vector<uint8_t> base(2048);
+            for (int lv = 0; lv < 3; lv++) {
+                build_quant_table(e->size_log2 - lv, lo.data(), hi.data(), base.data());
+                for (int c = 0; c < 2048; c++) tab[lv * 2048 + c] = make_uint2(lo[c], base[c] | ((hi[c] - lo[c]) << 8));
+            }
+            CU(cudaMalloc(&e->d_qtab, sizeof(uint2) * tab.size()));
+            CU(cudaMemcpy(e->d_qtab, tab.data(), sizeof(uint2) * tab.size(), cudaMemcpyHostToDevice));
+        }
+        return 0;
     case B200_OPT_PYRAMID_LAG:
         if (value < 1 || value > 8) return fail(B200_EINVAL, "pyramid lag must be 1..8 frames");
         e->opt_pyr_lag = value;
@@ -1714,6 +1777,12 @@ int b200_wait_block(b200_engine *e) {
 }
 
 uint64_t b200_launch_count(b200_engine *e) { return e ? e->launches : 0; }
+
+int b200_quant_table(int power_offset, uint32_t *lo, uint32_t *hi, uint8_t *base) {
+    if (!lo || !hi || !base) return fail(B200_EINVAL, "null argument");
+    build_quant_table(power_offset, lo, hi, base);
+    return 0;
+}
 
 int b200_debug_tail_profile(b200_engine *e, int enable, long long out[8]) {
     if (!e) return fail(B200_EINVAL, "null engine");

@@ -215,7 +215,8 @@ __device__ __forceinline__ unsigned and_or(unsigned a, unsigned b, unsigned c) {
     return d;
 }
 __device__ __forceinline__ float exponent_as_float(unsigned bits) { return __uint_as_float(and_or(bits >> 23, 0xFFu, 0x4B000000u)); }
-__device__ __forceinline__ float mantissa_1_2(unsigned bits) { return __uint_as_float(and_or(bits, 0x007FFFFFu, 0x3F800000u)); }
+// exponent field replaced by 127; the sign bit stays, as in the reference (`*bit_exponent &= ~(255 << 23)`, fft_impl.cpp:19)
+__device__ __forceinline__ float mantissa_1_2(unsigned bits) { return __uint_as_float(and_or(bits, 0x807FFFFFu, 0x3F800000u)); }
 __device__ __forceinline__ float vec_log2_biased(float val, float bias) {
     const unsigned bits = __float_as_uint(val);
     const float log_val = __fsub_rn(exponent_as_float(bits), bias);
@@ -274,10 +275,29 @@ __device__ __forceinline__ void quantize2_biased(float p0, float p1, float bias,
     t0 = __float2int_rz(fmaxf(__fadd_rn(vx, 127.f), -128.f));
     t1 = __float2int_rz(fmaxf(__fadd_rn(vy, 127.f), -128.f));
 }
+// Table-driven form (opt-in, B200_OPT_PACKED_MATH bit 1). Per power offset the quantiser is a step function of the 31
+// non-sign bits of the power with at most one step per 1/8 octave, except for a band of a few ulps around each step
+// where rounding makes it wiggle. tab[bits >> 20] = {lo, base | width << 8}: base below lo, base + 1 from lo + width on,
+// the exact arithmetic inside the band. Built by build_quant_table (engine.cu) with the reference arithmetic;
+// tools/quant_table.c checks the construction against all 2^31 inputs.
+__device__ __forceinline__ int quantize_table(float power, const uint2 *tab, float bias) {
+    const unsigned raw = __float_as_uint(power), b = raw & 0x7FFFFFFFu;
+    const uint2 e = __ldg(tab + (b >> 20));
+    const unsigned width = e.y >> 8;
+    int q = (int)(e.y & 0xFFu) + (b >= e.x + width ? 1 : 0);
+    // exact arithmetic inside the band (a handful of inputs per offset) and for a set sign bit (never for |X|^2; the
+    // reference's polynomial would see a negative mantissa)
+    if ((b - e.x < width) | (raw >> 31)) q = quantize_biased(power, bias);
+    return q;
+}
 // CNT bins of one level -> little-endian packed bytes in w[(CNT+3)/4]
-template <int CNT, bool PK> __device__ __forceinline__ void quantize_pack(const float *pw, float bias, unsigned *w) {
+template <int CNT, bool PK>
+__device__ __forceinline__ void quantize_pack(const float *pw, float bias, unsigned *w, const uint2 *tab = nullptr) {
     int t[CNT];
-    if constexpr (PK && CNT >= 2) {
+    if (tab) {
+#pragma unroll
+        for (int i = 0; i < CNT; i++) t[i] = quantize_table(pw[i], tab, bias);
+    } else if constexpr (PK && CNT >= 2) {
 #pragma unroll
         for (int i = 0; i < CNT; i += 2) quantize2_biased(pw[i], pw[i + 1], bias, t[i], t[i + 1]);
     } else {
@@ -472,6 +492,7 @@ struct PyrParams {
     int ntiles, N2;
     int npeers;
     float2 *peers[kMaxPeers];
+    const uint2 *qtab;       // optional [3][2048] quantiser tables of levels 0..2 (see quantize_table), or nullptr
 };
 
 // grid ((R >> base_level) / (256*PER), frames), block 256: each thread owns PER (4 or 16) consecutive entries of the
@@ -588,7 +609,7 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
         constexpr int CNT = PER >> lv;
         if (lv < L) {
             unsigned w[(CNT + 3) / 4];
-            quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w);
+            quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w, (p.qtab && B + lv < 3) ? p.qtab + 2048 * (B + lv) : nullptr);
             store_packed<CNT>(quant + lvl_off + (d0 >> lv), w);
         }
         lvl_off += RB_ >> lv;
