@@ -591,10 +591,12 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
             if (pk) pyramid_kernel<PYR_SCRATCH, 4, true><<<grid, 256, 0, e->stream>>>(q);
             else pyramid_kernel<PYR_SCRATCH, 4, false><<<grid, 256, 0, e->stream>>>(q);
         } else if (fuse == 2) {
-            if (pk) pyramid_kernel<PYR_POWER, 16, true><<<grid, 256, 0, e->stream>>>(q);
+            if (pk && q.qtab) pyramid_kernel<PYR_POWER, 16, true, true><<<grid, 256, 0, e->stream>>>(q);
+            else if (pk) pyramid_kernel<PYR_POWER, 16, true><<<grid, 256, 0, e->stream>>>(q);
             else pyramid_kernel<PYR_POWER, 16, false><<<grid, 256, 0, e->stream>>>(q);
         } else {
-            if (pk) pyramid_kernel<PYR_SPEC, 16, true><<<grid, 256, 0, e->stream>>>(q);
+            if (pk && q.qtab) pyramid_kernel<PYR_SPEC, 16, true, true><<<grid, 256, 0, e->stream>>>(q);
+            else if (pk) pyramid_kernel<PYR_SPEC, 16, true><<<grid, 256, 0, e->stream>>>(q);
             else pyramid_kernel<PYR_SPEC, 16, false><<<grid, 256, 0, e->stream>>>(q);
         }
         e->launches++;

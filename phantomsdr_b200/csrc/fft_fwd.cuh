@@ -504,7 +504,7 @@ struct CtaSync {
 // One block of 256 threads (a CTA of pyramid_kernel, or one consumer group of the fused FFT kernel): `blk` = block
 // index within the frame, `tid` = 0..255, `warp_sum_s` = 8 floats of shared memory, `sync` = barrier of those 256
 // threads. CG: spectrum loads bypass L1 (the fused kernel reads bins that other SMs stored during the same launch).
-template <int MODE, int PER, bool PK, bool CG, typename Sync>
+template <int MODE, int PER, bool PK, bool CG, bool TB = false, typename Sync = CtaSync>
 __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int frame, const unsigned blk, const int tid,
                                               float *warp_sum_s, Sync sync) {
     static_assert(PER == 4 || PER == 16, "PER must be 4 or 16");
@@ -609,7 +609,10 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
         constexpr int CNT = PER >> lv;
         if (lv < L) {
             unsigned w[(CNT + 3) / 4];
-            quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w, (p.qtab && B + lv < 3) ? p.qtab + 2048 * (B + lv) : nullptr);
+            if constexpr (TB)  // table-driven levels 0..2 (opt-in instantiation; the default kernels do not carry this path)
+                quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w, (p.qtab && B + lv < 3) ? p.qtab + 2048 * (B + lv) : nullptr);
+            else
+                quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w);
             store_packed<CNT>(quant + lvl_off + (d0 >> lv), w);
         }
         lvl_off += RB_ >> lv;
@@ -653,9 +656,9 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
     }
 }
 
-template <int MODE, int PER, bool PK> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+template <int MODE, int PER, bool PK, bool TB = false> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
     __shared__ float warp_sum_s[8];
-    pyramid_block<MODE, PER, PK, false>(p, blockIdx.y, blockIdx.x, threadIdx.x, warp_sum_s, CtaSync{});
+    pyramid_block<MODE, PER, PK, false, TB>(p, blockIdx.y, blockIdx.x, threadIdx.x, warp_sum_s, CtaSync{});
 }
 
 // more than ten levels above the base (only for very deep pyramids): one block per frame, pairwise tree over

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kP3Threads, 1)
         if (gt == 0) wait_counter(done + fp, (unsigned)tiles_per_frame);  // every bin of frame fp is stored and visible
         group_sync(g);
         for (int b = 0; b < count; b++) {
-            pyramid_block<PYR_SPEC, 16, true, true>(pyr, fp, (unsigned)(blk0 + b), gt, wsum + 8 * g, GroupSync{g});
+            pyramid_block<PYR_SPEC, 16, true, true, false>(pyr, fp, (unsigned)(blk0 + b), gt, wsum + 8 * g, GroupSync{g});
             group_sync(g);  // the block's warp sums are consumed before the next block overwrites them
         }
     };
