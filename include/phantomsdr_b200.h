@@ -119,7 +119,8 @@ int b200_execute(b200_engine *e);
                                    64 frames/launch, three-stage pass 2: 8.5 (mode 0) / 9.0 (mode 2) us per frame. */
 #define B200_OPT_TMA 6           /* 2^20-point transforms: 2 (default) = TMA-fed pass 1 + three-stage pass 2 (one CTA of two
                                    consumer groups per SM), 3 = same with the waterfall pyramid fused into pass 2 (per-frame
-                                   completion counters; experimental), 1 = two-CTA pass 2, 0 = generic kernels */
+                                   completion counters; measured slower), 4 = both passes in one persistent launch with Y as an
+                                   L2-resident ring (fft_fused.cuh; compiled, not yet run on a GPU), 1 = two-CTA pass 2, 0 = generic */
 #define B200_OPT_TAIL_PIPELINE 7 /* 1 (default): frame-skewed software pipeline for the DC/AGC tails when >= 4 frames per call */
 #define B200_OPT_PEER_STORES 8   /* 1 (default): FFT pass 2 stores the peers' sub-bands itself; 0: leave it to b200_push_peers */
 #define B200_OPT_PACKED_MATH 9   /* bit0 (default 1): waterfall quantiser on the packed-f32 pipe (FMUL2/FADD2), same IEEE rounding per lane;

@@ -18,6 +18,7 @@
 #include "clients.cuh"
 #include "fft_fwd.cuh"
 #include "fft_tma.cuh"
+#include "fft_fused.cuh"
 
 using namespace b200;
 
@@ -379,9 +380,10 @@ int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
+    CU(cudaFuncSetAttribute(fft_fused12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem::kTotal));
     if (!e->d_done) {
-        CU(cudaMalloc(&e->d_done, sizeof(unsigned) * 4 * 64));  // per-frame tile counters of the fused kernel, one row per lane
-        CU(cudaMemset(e->d_done, 0, sizeof(unsigned) * 4 * 64));
+        CU(cudaMalloc(&e->d_done, sizeof(unsigned) * 4 * 128));  // per-frame tile counters of the fused kernels: per lane 64 + 64
+        CU(cudaMemset(e->d_done, 0, sizeof(unsigned) * 4 * 128));
     }
     e->tma_ok = true;
     return 0;
@@ -414,7 +416,7 @@ int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse, c
         const bool peers = p.npeers > 0;
         PyrParams none{};
         if (pyr) {  // spectrum + whole pyramid in one launch (FUSE 3): zero the per-frame tile counters first
-            unsigned *done = e->d_done + 64 * lane;
+            unsigned *done = e->d_done + 128 * lane;
             CU(cudaMemsetAsync(done, 0, sizeof(unsigned) * 64, e->stream));
             const int lag = std::max(1, e->opt_pyr_lag);
             if (!peers) fft_pass2_tma3_kernel<3, false><<<grid, kP3Threads, P3Smem::kTotal, e->stream>>>(p, frames, *pyr, done, lag);
@@ -553,7 +555,7 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     q.qtab = (e->opt_packed & 2) ? e->d_qtab : nullptr;
     for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i] + (size_t)f0 * e->spec_stride;
     // opt_tma 3: pass 2 of the TMA path also produces the whole pyramid (FUSE 3), unless a stage is masked out for profiling
-    const bool fused = tma && e->opt_tma >= 3 && fuse == 0 && !e->is_real && e->na == 1 && (e->opt_packed & 1) &&
+    const bool fused = tma && e->opt_tma == 3 && fuse == 0 && !e->is_real && e->na == 1 && (e->opt_packed & 1) &&
                        (e->opt_stage_mask & 6) == 6 && frames <= 64 && e->levels > 0 &&
                        e->opt_lanes <= 1;  // its CTAs wait on one another: never two such grids competing for the SMs
     if (e->na > 1) {
@@ -564,6 +566,16 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         if (rc) return rc;
         if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames * e->na, 0);
         if (rc) return rc;
+    } else if (tma && e->opt_tma == 4 && !e->is_real && fuse == 0 && p.npeers == 0 && frames >= 2 && frames <= 64 &&
+               e->num_sms >= kS / kTmaT && e->opt_lanes <= 1 && (e->opt_stage_mask & 3) == 3) {
+        // EXPERIMENTAL: both passes in one persistent launch, Y as an L2-resident ring of K frame slots (fft_fused.cuh)
+        unsigned *done = e->d_done + 128 * lane;
+        CU(cudaMemsetAsync(done, 0, sizeof(unsigned) * 128, e->stream));
+        const int K = std::min(8, frames);
+        fft_fused12_kernel<<<e->num_sms, kP3Threads, FusedSmem::kTotal, e->stream>>>(p, e->ring_map, e->window_map, frames, K, done,
+                                                                                      done + 64);
+        e->launches++;
+        CU(cudaGetLastError());
     } else {
         if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
         if (rc) return rc;
@@ -1121,7 +1133,7 @@ int b200_set_option(b200_engine *e, int option, int value) {
         if (value < -1 || value > 2) return fail(B200_EINVAL, "fused pyramid mode must be -1 (auto), 0, 1 or 2");
         e->opt_fused_pyramid = value;
         return 0;
-    case B200_OPT_TMA: e->opt_tma = value < 0 ? 0 : (value > 3 ? 3 : value); return 0;
+    case B200_OPT_TMA: e->opt_tma = value < 0 ? 0 : (value > 4 ? 4 : value); return 0;
     case B200_OPT_PEER_STORES: e->opt_peer_stores = value ? 1 : 0; return 0;
     case B200_OPT_TAIL_PIPELINE: e->opt_tail_pipe = value ? 1 : 0; return 0;
     case B200_OPT_PACKED_MATH:
