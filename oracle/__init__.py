@@ -24,6 +24,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "liboracle.so"
 REF_PATH = HERE / "_ref" / "libphantom_ref.so"
+REF_FFT_PATH = HERE / "_ref" / "libphantom_ref_fft.so"
 
 USB, LSB, AM, FM = 0, 1, 2, 3  # src/client.h:43
 MODE_NAMES = {USB: "USB", LSB: "LSB", AM: "AM", FM: "FM"}
@@ -39,8 +40,9 @@ def build(force: bool = False) -> None:
     if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < src_mtime:
         subprocess.check_call(["make", "-s", "-C", str(HERE), str(LIB_PATH)])
     if Path("/root/reference/src/utils").is_dir():
-        shim_mtime = max((HERE / f).stat().st_mtime for f in ("ref_shim.cpp", "Makefile"))
-        if force or not REF_PATH.exists() or REF_PATH.stat().st_mtime < shim_mtime:
+        shim_mtime = max((HERE / f).stat().st_mtime for f in ("ref_shim.cpp", "ref_shim_fft.cpp", "Makefile"))
+        if force or not REF_PATH.exists() or not REF_FFT_PATH.exists() or \
+                min(REF_PATH.stat().st_mtime, REF_FFT_PATH.stat().st_mtime) < shim_mtime:
             subprocess.check_call(["make", "-s", "-C", str(HERE), "ref"])
 
 
@@ -153,6 +155,47 @@ def ref():
         fn.restype = res
         fn.argtypes = args
     _ref = R
+    return R
+
+
+_ref_fft = None
+
+
+def ref_fft():
+    """The reference's own src/fft_impl.cpp (class FFTW) and src/signal.cpp (AudioClient::send_audio) compiled against
+    stand-in third-party headers (oracle/ref_shim_fft.cpp), or None if not built. The DFT behind fftwf_execute is the
+    oracle's own (FFTW3f is absent), so everything around the transforms compares bit for bit."""
+    global _ref_fft
+    if _ref_fft is not None:
+        return _ref_fft
+    if not REF_FFT_PATH.exists():
+        return None
+    R = C.CDLL(str(REF_FFT_PATH))
+    vp, sz, i, f, d = C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_double
+    sig = {
+        "ref_set_dft": (None, [vp]),
+        "ref_fftw_create": (vp, [sz, i, i, sz, i]),
+        "ref_fftw_destroy": (None, [vp]),
+        "ref_fftw_load_real": (None, [vp, _f32p, _f32p]),
+        "ref_fftw_load_complex": (None, [vp, _f32p, _f32p]),
+        "ref_fftw_execute": (None, [vp]),
+        "ref_fftw_input": (vp, [vp]),
+        "ref_fftw_output": (vp, [vp]),
+        "ref_fftw_quantized": (vp, [vp]),
+        "ref_audio_create": (vp, [i, i, i, i]),
+        "ref_audio_destroy": (None, [vp]),
+        "ref_audio_set_range": (None, [vp, i, d, i]),
+        "ref_audio_set_demodulation": (None, [vp, i]),
+        "ref_audio_on_demodulation_message": (None, [vp, C.c_char_p]),
+        "ref_audio_on_window_message": (i, [vp, i, d, i]),
+        "ref_audio_send": (i, [vp, vp, sz, _i32p, _f32p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(R, name)
+        fn.restype = res
+        fn.argtypes = args
+    R.ref_set_dft(C.cast(lib().orc_dft_f32, vp))  # both sides transform with the same arithmetic
+    _ref_fft = R
     return R
 
 

@@ -660,12 +660,13 @@ ORC_API int orc_client_send_audio(orc_client *c, const float *buf, size_t frame_
     const int is_real = c->is_real;
     int len = audio_r - audio_l;
 
-    /* signal.cpp:117-119 - std::accumulate of std::norm; libstdc++'s norm() for floating
-       types without -ffast-math is abs(z)^2, i.e. hypotf squared */
+    /* signal.cpp:117-119 - std::accumulate of std::norm. libstdc++'s norm() for floating types is
+       re*re + im*im (bits/complex: _Norm_helper, the abs()^2 form is commented out there); pinned bit for
+       bit against the reference's compiled send_audio by tests/test_oracle_vs_ref_fft.py */
     float average_power = 0.0f;
     for (int i = 0; i < len; i++) {
-        float a = hypotf(buf[2 * i], buf[2 * i + 1]);
-        average_power = average_power + a * a;
+        float re = buf[2 * i], im = buf[2 * i + 1];
+        average_power = average_power + (re * re + im * im);
     }
 
     float *in = c->audio_fft_input;

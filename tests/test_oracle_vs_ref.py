@@ -97,14 +97,13 @@ def test_dc_blocker_bit_exact(delay):
     ref.ref_dc_destroy(r)
 
 
-def test_slice_power_is_hypot_squared():
-    """std::norm on complex<float> without -ffast-math is abs()^2 (libstdc++), which is what the oracle's
-    pwr accumulation restates (src/signal.cpp:117-119)."""
+def test_slice_power_is_re2_plus_im2():
+    """std::norm on complex<float> is re*re + im*im in libstdc++ (not abs()^2); the oracle's pwr accumulation restates
+    that (src/signal.cpp:117-119). Bit-exact."""
     rng = np.random.default_rng(6)
     z = (rng.standard_normal(2 * 90) * 1e-3).astype(f32)
     want = ref.ref_slice_power(z.copy(), 90)
     acc = f32(0)
     for i in range(90):
-        a = f32(np.hypot(z[2 * i], z[2 * i + 1]))
-        acc = f32(acc + f32(a * a))
-    assert abs(want - acc) <= 2e-7 * abs(acc)
+        acc = f32(acc + f32(f32(z[2 * i] * z[2 * i]) + f32(z[2 * i + 1] * z[2 * i + 1])))
+    assert want == acc

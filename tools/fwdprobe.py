@@ -1,5 +1,5 @@
 """Forward-group variants: bit-for-bit comparison against the first variant, then per-stage timings (edit VARIANTS).
-Usage: python tools/fwdprobe.py [batch]"""
+Usage: python tools/fwdprobe.py [batch] [name substrings...]"""
 import sys
 sys.path.insert(0, '.')
 import torch
@@ -65,7 +65,11 @@ VARIANTS = [
     ("sub-batches of 8", {OPT_FWD_SUB_FRAMES: 8}),
     ("tma3 fused lag1", {OPT_TMA: 3, OPT_PYRAMID_LAG: 1}),
     ("tma3 fused lag2", {OPT_TMA: 3, OPT_PYRAMID_LAG: 2}),
+    ("table quantiser", {OPT_PACKED_MATH: 3}),
+    ("fused12 (tma 4)", {OPT_TMA: 4}),
 ]
+if len(sys.argv) > 2:  # keep the reference variant plus those whose name contains one of the given substrings
+    VARIANTS = [VARIANTS[0]] + [v for v in VARIANTS[1:] if any(k in v[0] for k in sys.argv[2:])]
 ref = None
 for name, opts in VARIANTS:
     if F < 16 and opts.get(OPT_FWD_SUB_FRAMES, 64) * opts.get(OPT_FWD_LANES, 1) > F:
