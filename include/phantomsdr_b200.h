@@ -119,8 +119,9 @@ int b200_execute(b200_engine *e);
                                    64 frames/launch, three-stage pass 2: 8.5 (mode 0) / 9.0 (mode 2) us per frame. */
 #define B200_OPT_TMA 6           /* 2^20-point transforms: 2 (default) = TMA-fed pass 1 + three-stage pass 2 (one CTA of two
                                    consumer groups per SM), 3 = same with the waterfall pyramid fused into pass 2 (per-frame
-                                   completion counters; measured slower), 4 = both passes in one persistent launch with Y as an
-                                   L2-resident ring (fft_fused.cuh; compiled, not yet run on a GPU), 1 = two-CTA pass 2, 0 = generic */
+                                   completion counters; measured slower), 4 = c2c: pass 1, pass 2 and the pyramid of consecutive frames
+                                   in ONE persistent dataflow-scheduled launch (fft_stream.cuh: the four-step intermediate and the
+                                   spectrum the quantiser reads stay in L2), 1 = two-CTA pass 2, 0 = generic */
 #define B200_OPT_TAIL_PIPELINE 7 /* 1 (default): frame-skewed software pipeline for the DC/AGC tails when >= 4 frames per call */
 #define B200_OPT_PEER_STORES 8   /* 1 (default): FFT pass 2 stores the peers' sub-bands itself; 0: leave it to b200_push_peers */
 #define B200_OPT_PACKED_MATH 9   /* bit0 (default 1): waterfall quantiser on the packed-f32 pipe (FMUL2/FADD2), same IEEE rounding per lane;
@@ -129,6 +130,10 @@ int b200_execute(b200_engine *e);
 #define B200_OPT_FWD_SUB_FRAMES 11 /* frames per forward launch group inside a device batch (default: the whole batch) */
 #define B200_OPT_PASS1_ORDER 12  /* tuning: work-item order of the TMA pass 1 (0 default: column tile sticky, frames swept together) */
 #define B200_OPT_PYRAMID_LAG 13  /* B200_OPT_TMA 3: frames between a pass-2 tile and the pyramid blocks that ride on it (default 2) */
+#define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */
+#define B200_OPT_STREAM_LAG1 15  /* ... frame slots between pass 1 and pass 2 of a frame in the item order (default 2) */
+#define B200_OPT_STREAM_LAG2 16  /* ... between pass 1 and the quantiser (default 4) */
+#define B200_OPT_STREAM_RING 17  /* ... frame slots of the L2-resident ring that holds the four-step intermediate (default 5) */
 #define B200_OPT_STAGE_MASK 4    /* profiling aid: bit0 = FFT pass 1, bit1 = pass 2, bit2 = pyramid; default 7 */
 int b200_set_option(b200_engine *e, int option, int value);
 

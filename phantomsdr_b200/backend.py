@@ -23,6 +23,7 @@ FMT_F32, FMT_U8, FMT_S8, FMT_U16, FMT_S16 = 0, 1, 2, 3, 4
 OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_TAIL_PIPELINE, OPT_PEER_STORES = 1, 2, 3, 4, 5, 6, 7, 8
 OPT_PACKED_MATH, OPT_FWD_LANES, OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER = 9, 10, 11, 12
 OPT_PYRAMID_LAG = 13
+OPT_STREAM_GRID, OPT_STREAM_LAG1, OPT_STREAM_LAG2, OPT_STREAM_RING = 14, 15, 16, 17
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 

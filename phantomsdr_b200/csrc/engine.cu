@@ -18,7 +18,7 @@
 #include "clients.cuh"
 #include "fft_fwd.cuh"
 #include "fft_tma.cuh"
-#include "fft_fused.cuh"
+#include "fft_stream.cuh"
 
 using namespace b200;
 
@@ -200,6 +200,20 @@ struct b200_engine {
     bool tma_ok = false;
     int num_sms = 148;
     CUtensorMap ring_map{}, window_map{};
+    // dataflow-scheduled forward group (fft_stream.cuh, B200_OPT_TMA 4)
+    CUtensorMap spec_map{};             // the spectrum as rows of 16 bins from bin 1, 128-byte swizzle (quantiser items)
+    bool spec_map_ok = false;
+    StreamSync *d_ssync = nullptr;
+    unsigned *h_abort = nullptr;        // pinned mirror of StreamSync::abort, refreshed behind every launch
+    float2 *d_winT = nullptr;
+    unsigned *d_items = nullptr;
+    int *d_nitems = nullptr;
+    int items_frames = -1, items_grid = 0, items_lag1 = 0, items_lag2 = 0, items_max = 0, items_mask = 7;
+    int opt_stream_grid = 0;            // CTAs of the stream kernel (0 = one per SM)
+    int opt_stream_lag1 = 2;            // frame slots between pass 1 and pass 2 of a frame in the item order
+    int opt_stream_lag2 = 4;            // ... between pass 1 and the quantiser
+    int opt_stream_ring = 5;            // Y ring slots
+    bool stream_used = false;
 
     int npeers = 0;
     float2 *peers[kMaxPeers] = {};
@@ -344,7 +358,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // 2-D uint32 tensor {inner, rows} with row pitch = inner * 4 bytes, box {box_inner, 256}
-int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t rows, uint32_t box_inner) {
+int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t rows, uint32_t box_inner, bool swizzle128 = false) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {inner, rows};
@@ -352,7 +366,8 @@ int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t rows, uin
     cuuint32_t box[2] = {box_inner, 256};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(B200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
@@ -380,7 +395,25 @@ int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
     CU(cudaFuncSetAttribute(fft_pass2_tma3_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P3Smem::kTotal));
-    CU(cudaFuncSetAttribute(fft_fused12_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem::kTotal));
+    if (!e->is_real) {
+        CU(cudaFuncSetAttribute(fwd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamSmem::kTotal));
+        CU(cudaFuncSetAttribute(fwd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)StreamSmem::kTotal));
+        if (!e->d_ssync) {
+            CU(cudaMalloc(&e->d_ssync, sizeof(StreamSync)));
+            CU(cudaMemset(e->d_ssync, 0, sizeof(StreamSync)));
+            CU(cudaHostAlloc(&e->h_abort, sizeof(unsigned), cudaHostAllocDefault));
+            *e->h_abort = 0;
+            // window table of pass 1: (h cos, h sin)(2 pi row / 1024), h = 1 / (2 size) (the 1/N normalisation rides on the window)
+            std::vector<float2> wt(kS);
+            const double h = 0.5 / (double)e->size;
+            for (int r = 0; r < kS; r++) {
+                const double a = 2.0 * M_PI * (double)r / kS;
+                wt[r] = make_float2((float)(h * cos(a)), (float)(h * sin(a)));
+            }
+            e->d_winT = upload_f2(wt);
+            if (!e->d_winT) return fail(B200_ENOMEM, "window table allocation failed");
+        }
+    }
     if (!e->d_done) {
         CU(cudaMalloc(&e->d_done, sizeof(unsigned) * 4 * 128));  // per-frame tile counters of the fused kernels: per lane 64 + 64
         CU(cudaMemset(e->d_done, 0, sizeof(unsigned) * 4 * 128));
@@ -467,6 +500,93 @@ int bank_acquire(b200_engine *e) {
         CU(cudaStreamWaitEvent(e->stream, e->ev_push[e->cur_bank], 0));
         e->push_pending[e->cur_bank] = false;
     }
+    return 0;
+}
+
+// ---- dataflow-scheduled forward group (fft_stream.cuh) ----------------------------------------------------------
+bool stream_path(const b200_engine *e) {
+    return e->opt_tma == 4 && e->tma_ok && e->spec_map_ok && e->d_ssync && e->log2M == 20 && e->na == 1 && !e->is_real &&
+           e->in_format == B200_FMT_F32 && !e->spec_bound && e->levels <= 13 && (e->opt_packed & 1) &&
+           e->opt_lanes <= 1 && e->num_sms >= 8;
+}
+// The global item list - frame slot s: the 128 pass-1 tiles of frame s, the 128 pass-2 tiles of frame s - lag1, the 128
+// quantiser chunks of frame s - lag2 - dealt round-robin to the CTAs (items of frames outside the batch are left out
+// BEFORE dealing, so the CTAs stay balanced through the prologue and the epilogue).
+int stream_items(b200_engine *e, int frames, int grid) {
+    const int lag1 = e->opt_stream_lag1, lag2 = std::max(e->opt_stream_lag2, lag1);
+    const int mask = e->opt_stage_mask & 7;
+    if (e->items_frames == frames && e->items_grid == grid && e->items_lag1 == lag1 && e->items_lag2 == lag2 && e->items_mask == mask)
+        return 0;
+    constexpr int NT = kS / kTmaT;
+    std::vector<std::vector<unsigned>> lists(grid);
+    size_t i = 0;
+    for (int s = 0; s < frames + lag2; s++) {
+        const int lag[3] = {0, lag1, lag2};
+        for (int type = 0; type < 3; type++) {
+            const int f = s - lag[type];
+            if (f < 0 || f >= frames || !(mask & (1 << type))) continue;
+            for (int t = 0; t < NT; t++) lists[i++ % grid].push_back(stream_item(type, f, t));
+        }
+    }
+    size_t mx = 1;
+    for (auto &l : lists) mx = std::max(mx, l.size());
+    std::vector<unsigned> flat((size_t)grid * mx, 0u);
+    std::vector<int> counts(grid);
+    for (int c = 0; c < grid; c++) {
+        counts[c] = (int)lists[c].size();
+        std::copy(lists[c].begin(), lists[c].end(), flat.begin() + (size_t)c * mx);
+    }
+    // the previous table may still be read by a launch in flight
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->d_items) cudaFree(e->d_items);
+    if (e->d_nitems) cudaFree(e->d_nitems);
+    e->d_items = nullptr;
+    e->d_nitems = nullptr;
+    CU(cudaMalloc(&e->d_items, sizeof(unsigned) * flat.size()));
+    CU(cudaMalloc(&e->d_nitems, sizeof(int) * grid));
+    CU(cudaMemcpy(e->d_items, flat.data(), sizeof(unsigned) * flat.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_nitems, counts.data(), sizeof(int) * grid, cudaMemcpyHostToDevice));
+    e->items_frames = frames;
+    e->items_grid = grid;
+    e->items_lag1 = lag1;
+    e->items_lag2 = lag2;
+    e->items_mask = mask;
+    e->items_max = (int)mx;
+    return 0;
+}
+int launch_stream(b200_engine *e, const FwdParams &p, const PyrParams &q, int f0, int frames) {
+    const int grid = std::max(1, std::min(e->opt_stream_grid > 0 ? e->opt_stream_grid : e->num_sms, e->num_sms));
+    int rc = stream_items(e, frames, grid);
+    if (rc) return rc;
+    StreamParams sp{};
+    sp.fp = p;
+    sp.pyr = q;
+    sp.items = e->d_items;
+    sp.nitems = e->d_nitems;
+    sp.max_items = e->items_max;
+    sp.K = std::max(1, std::min(e->opt_stream_ring, e->batch));
+    sp.nframes = frames;
+    sp.winT = e->d_winT;
+    sp.whalf = 0.5f / (float)e->size;
+    sp.spec_rows_per_frame = (unsigned)(e->spec_stride / 16);
+    sp.spec_row0 = (unsigned)(((size_t)e->cur_bank * e->batch + f0) * e->spec_stride / 16);
+    sp.nodeps = (e->opt_stage_mask & 7) != 7;
+    sp.sync = e->d_ssync;
+    CU(cudaMemsetAsync(e->d_ssync, 0, sizeof(unsigned) * 128, e->stream));  // the counters; the abort flag is sticky
+    if (p.npeers > 0)
+        fwd_stream_kernel<true><<<grid, kP3Threads, StreamSmem::kTotal, e->stream>>>(sp, e->ring_map, e->spec_map);
+    else
+        fwd_stream_kernel<false><<<grid, kP3Threads, StreamSmem::kTotal, e->stream>>>(sp, e->ring_map, e->spec_map);
+    e->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_abort, &e->d_ssync->abort, sizeof(unsigned), cudaMemcpyDeviceToHost, e->stream));
+    e->stream_used = true;
+    return 0;
+}
+// after a synchronisation point: did a bounded wait inside the stream kernel expire?
+int stream_check(b200_engine *e) {
+    if (e->stream_used && e->h_abort && *e->h_abort)
+        return fail(B200_ECUDA, "forward stream kernel: a bounded wait expired (protocol timeout); results of the batch are incomplete");
     return 0;
 }
 
@@ -566,16 +686,10 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         if (rc) return rc;
         if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames * e->na, 0);
         if (rc) return rc;
-    } else if (tma && e->opt_tma == 4 && !e->is_real && fuse == 0 && p.npeers == 0 && frames >= 2 && frames <= 64 &&
-               e->num_sms >= kS / kTmaT && e->opt_lanes <= 1 && (e->opt_stage_mask & 3) == 3) {
-        // EXPERIMENTAL: both passes in one persistent launch, Y as an L2-resident ring of K frame slots (fft_fused.cuh)
-        unsigned *done = e->d_done + 128 * lane;
-        CU(cudaMemsetAsync(done, 0, sizeof(unsigned) * 128, e->stream));
-        const int K = std::min(8, frames);
-        fft_fused12_kernel<<<e->num_sms, kP3Threads, FusedSmem::kTotal, e->stream>>>(p, e->ring_map, e->window_map, frames, K, done,
-                                                                                      done + 64);
-        e->launches++;
-        CU(cudaGetLastError());
+    } else if (stream_path(e) && frames <= 64) {
+        // all three stages in one persistent, dataflow-scheduled launch (fft_stream.cuh): Y and the spectrum a quantiser
+        // item reads never leave L2. The 1/N normalisation rides on pass 1's window table.
+        return launch_stream(e, p, q, f0, frames);
     } else {
         if (e->opt_stage_mask & 1) rc = tma ? launch_tma_pass1(e, p, frames) : dispatch_pass1(e, p, frames);
         if (rc) return rc;
@@ -771,6 +885,12 @@ int alloc_batch(b200_engine *e, int frames) {
     CU(cudaMalloc(&e->d_spec_raw, sizeof(float2) * (e->spec_stride * frames * e->banks + 16)));
     CU(cudaMemset(e->d_spec_raw, 0, sizeof(float2) * (e->spec_stride * frames * e->banks + 16)));
     e->d_spec = e->d_spec_raw + 15;
+    e->spec_map_ok = false;
+    if (e->tma_ok && !e->is_real && e->spec_stride % 16 == 0) {
+        // quantiser items of the stream kernel read the spectrum as rows of 16 bins starting at bin 1 (a 128-byte line)
+        const uint64_t rows = (uint64_t)e->spec_stride * frames * e->banks / 16;
+        if (make_map_2d(&e->spec_map, e->d_spec + 1, 32, rows, 32, true) == 0) e->spec_map_ok = true;
+    }
     CU(cudaMalloc(&e->d_quant, e->pyr_stride * frames * e->banks));
     CU(cudaMemset(e->d_quant, 0, e->pyr_stride * frames * e->banks));
     e->cur_bank = 0;
@@ -1014,7 +1134,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
+    void *dev[] = {e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_qtab, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
@@ -1023,6 +1143,10 @@ void b200_engine_destroy(b200_engine *e) {
         if (p) cudaFree(p);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_quant) cudaFreeHost(e->h_quant);
+    if (e->h_abort) cudaFreeHost(e->h_abort);
+    if (e->ev_fwd_done) cudaEventDestroy(e->ev_fwd_done);
+    for (int b = 0; b < 4; b++)
+        if (e->ev_push[b]) cudaEventDestroy(e->ev_push[b]);
     if (e->cstream) {
         cudaStreamSynchronize(e->cstream);
         for (int b = 0; b < 4; b++) {
@@ -1168,6 +1292,22 @@ int b200_set_option(b200_engine *e, int option, int value) {
         if (value < 1 || value > 64) return fail(B200_EINVAL, "sub-batch frames must be 1..64");
         e->opt_sub_frames = value;
         return 0;
+    case B200_OPT_STREAM_GRID:
+        if (value < 0 || value > 1024) return fail(B200_EINVAL, "stream grid must be 0 (one CTA per SM) .. 1024");
+        e->opt_stream_grid = value;
+        return 0;
+    case B200_OPT_STREAM_LAG1:
+        if (value < 0 || value > 16) return fail(B200_EINVAL, "stream lag must be 0..16 frames");
+        e->opt_stream_lag1 = value;
+        return 0;
+    case B200_OPT_STREAM_LAG2:
+        if (value < 0 || value > 32) return fail(B200_EINVAL, "stream lag must be 0..32 frames");
+        e->opt_stream_lag2 = value;
+        return 0;
+    case B200_OPT_STREAM_RING:
+        if (value < 1 || value > 64) return fail(B200_EINVAL, "Y ring must be 1..64 frame slots");
+        e->opt_stream_ring = value;
+        return 0;
     case B200_OPT_INPUT_FORMAT:
         if (value < B200_FMT_F32 || value > B200_FMT_S16) return fail(B200_EINVAL, "unknown input format %d", value);
         if (value != e->in_format) {
@@ -1194,7 +1334,7 @@ int b200_execute(b200_engine *e) {
     if (e->opt_mirror & 2)
         CU(cudaMemcpyAsync(e->h_quant, e->quant_ptr(), e->pyr_bytes, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    return 0;
+    return stream_check(e);
 }
 
 void *b200_device_spectrum(b200_engine *e) { return e ? e->spec_ptr() : nullptr; }
@@ -1241,7 +1381,7 @@ int b200_sync(b200_engine *e) {
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
     if (e->cstream) CU(cudaStreamSynchronize(e->cstream));
-    return 0;
+    return stream_check(e);
 }
 int b200_set_pipeline(b200_engine *e, int banks) {
     if (!e) return fail(B200_EINVAL, "null engine");
@@ -1787,7 +1927,7 @@ int b200_wait_block(b200_engine *e) {
     CU(cudaEventSynchronize(e->ev_out[slot]));
     e->blk_pending[slot] = false;
     e->blk_waited++;
-    return 0;
+    return stream_check(e);
 }
 
 uint64_t b200_launch_count(b200_engine *e) { return e ? e->launches : 0; }

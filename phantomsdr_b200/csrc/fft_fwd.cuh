@@ -501,6 +501,74 @@ struct PyrParams {
 struct CtaSync {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
+// The pairwise-sum tree over one block of 256 * PER base-level entries whose powers are already in registers
+// (pw[i] = entry (blk * 256 + tid) * PER + i of level B): quantises and stores every level the block covers.
+template <int PER, bool PK, bool TB = false, typename Sync = CtaSync>
+__device__ __forceinline__ void pyramid_tree(const PyrParams &p, const int frame, const unsigned blk, const int tid, float (&pw)[PER],
+                                             const int B, float *warp_sum_s, Sync sync) {
+    constexpr int LP = (PER == 16) ? 4 : 2;  // levels reduced in registers
+    const unsigned R = 1u << p.log2R;
+    const unsigned d0 = (blk * 256u + tid) * PER;  // index at level B
+    int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
+    const int L = p.levels - B;  // levels still to produce, counted from the base
+    const int off = p.size_log2 - B;
+    unsigned lvl_off = 0;        // byte offset of level B
+    for (int i = 0; i < B; i++) lvl_off += R >> i;
+    const unsigned RB_ = R >> B;   // entries at the base level
+    if (L <= 0) return;
+    // relative levels 0 .. LP in registers: level lv has PER >> lv values per thread, stored as one word/vector
+    static_for<LP + 1>([&](auto lvc) {
+        constexpr int lv = decltype(lvc)::value;
+        constexpr int CNT = PER >> lv;
+        if (lv < L) {
+            unsigned w[(CNT + 3) / 4];
+            if constexpr (TB)  // table-driven levels 0..2 (opt-in instantiation; the default kernels do not carry this path)
+                quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w, (p.qtab && B + lv < 3) ? p.qtab + 2048 * (B + lv) : nullptr);
+            else
+                quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w);
+            store_packed<CNT>(quant + lvl_off + (d0 >> lv), w);
+        }
+        lvl_off += RB_ >> lv;
+        if constexpr (CNT > 1) {
+#pragma unroll
+            for (int i = 0; i < CNT / 2; i++) pw[i] = __fadd_rn(pw[2 * i], pw[2 * i + 1]);
+        }
+    });
+    // pw[0] now holds the thread's level-LP sum (already written above)
+    if (L > LP + 1) {
+        float s = pw[0];
+        const int lane = tid & 31;
+#pragma unroll
+        for (int k = 1; k <= 5; k++) {  // relative levels LP+1 .. LP+5 inside the warp
+            const int lv = LP + k;
+            if (lv < L) {
+                s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1 << (k - 1)));
+                if ((lane & ((1 << k) - 1)) == 0) quant[lvl_off + (d0 >> lv)] = (int8_t)quantize_dev(s, off - lv);
+                lvl_off += RB_ >> lv;
+            }
+        }
+        if (L > LP + 6) {
+            if (lane == 0) warp_sum_s[tid >> 5] = s;
+            sync();
+            if (tid < 8) {
+                float w = warp_sum_s[tid];
+                const unsigned b0 = blk * 256u * PER;
+#pragma unroll
+                for (int k = 1; k <= 3; k++) {  // relative levels LP+6 .. LP+8 across the eight warps
+                    const int lv = LP + 5 + k;
+                    if (lv < L) {
+                        w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (k - 1)));
+                        if ((tid & ((1 << k) - 1)) == 0)
+                            quant[lvl_off + ((b0 + 32u * PER * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
+                        lvl_off += RB_ >> lv;
+                    }
+                }
+                if (L > LP + 9 && tid == 0) p.ptop[(size_t)frame * (RB_ / (256 * PER)) + blk] = w;
+            }
+        }
+    }
+}
+
 // One block of 256 threads (a CTA of pyramid_kernel, or one consumer group of the fused FFT kernel): `blk` = block
 // index within the frame, `tid` = 0..255, `warp_sum_s` = 8 floats of shared memory, `sync` = barrier of those 256
 // threads. CG: spectrum loads bypass L1 (the fused kernel reads bins that other SMs stored during the same launch).
@@ -597,63 +665,7 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
             pw[i] = scr[tile * p.N2 + d2];
         }
     }
-    const int L = p.levels - B;  // levels still to produce, counted from the base
-    const int off = p.size_log2 - B;
-    unsigned lvl_off = 0;        // byte offset of level B
-    for (int i = 0; i < B; i++) lvl_off += R >> i;
-    const unsigned RB_ = R >> B;   // entries at the base level
-    if (L <= 0) return;
-    // relative levels 0 .. LP in registers: level lv has PER >> lv values per thread, stored as one word/vector
-    static_for<LP + 1>([&](auto lvc) {
-        constexpr int lv = decltype(lvc)::value;
-        constexpr int CNT = PER >> lv;
-        if (lv < L) {
-            unsigned w[(CNT + 3) / 4];
-            if constexpr (TB)  // table-driven levels 0..2 (opt-in instantiation; the default kernels do not carry this path)
-                quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w, (p.qtab && B + lv < 3) ? p.qtab + 2048 * (B + lv) : nullptr);
-            else
-                quantize_pack<CNT, PK>(pw, quant_bias(off - lv), w);
-            store_packed<CNT>(quant + lvl_off + (d0 >> lv), w);
-        }
-        lvl_off += RB_ >> lv;
-        if constexpr (CNT > 1) {
-#pragma unroll
-            for (int i = 0; i < CNT / 2; i++) pw[i] = __fadd_rn(pw[2 * i], pw[2 * i + 1]);
-        }
-    });
-    // pw[0] now holds the thread's level-LP sum (already written above)
-    if (L > LP + 1) {
-        float s = pw[0];
-        const int lane = tid & 31;
-#pragma unroll
-        for (int k = 1; k <= 5; k++) {  // relative levels LP+1 .. LP+5 inside the warp
-            const int lv = LP + k;
-            if (lv < L) {
-                s = __fadd_rn(s, __shfl_xor_sync(0xffffffffu, s, 1 << (k - 1)));
-                if ((lane & ((1 << k) - 1)) == 0) quant[lvl_off + (d0 >> lv)] = (int8_t)quantize_dev(s, off - lv);
-                lvl_off += RB_ >> lv;
-            }
-        }
-        if (L > LP + 6) {
-            if (lane == 0) warp_sum_s[tid >> 5] = s;
-            sync();
-            if (tid < 8) {
-                float w = warp_sum_s[tid];
-                const unsigned b0 = blk * 256u * PER;
-#pragma unroll
-                for (int k = 1; k <= 3; k++) {  // relative levels LP+6 .. LP+8 across the eight warps
-                    const int lv = LP + 5 + k;
-                    if (lv < L) {
-                        w = __fadd_rn(w, __shfl_xor_sync(0xffu, w, 1 << (k - 1)));
-                        if ((tid & ((1 << k) - 1)) == 0)
-                            quant[lvl_off + ((b0 + 32u * PER * tid) >> lv)] = (int8_t)quantize_dev(w, off - lv);
-                        lvl_off += RB_ >> lv;
-                    }
-                }
-                if (L > LP + 9 && tid == 0) p.ptop[(size_t)frame * (RB_ / (256 * PER)) + blk] = w;
-            }
-        }
-    }
+    pyramid_tree<PER, PK, TB>(p, frame, blk, tid, pw, B, warp_sum_s, sync);
 }
 
 template <int MODE, int PER, bool PK, bool TB = false> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {

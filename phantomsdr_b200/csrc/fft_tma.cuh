@@ -44,6 +44,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {  // non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // A transfer that never lands would be a bug in this file; rather than hang the GPU, a wait that has lasted more
 // than five seconds of wall time (globaltimer, checked every 4096 failed attempts) traps.
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -74,6 +87,9 @@ __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// orders what this thread has observed of global memory (through an acquire) and its shared-memory accesses before its
+// subsequent TMA (async proxy) operations
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { __syncthreads(); }
 
