@@ -296,7 +296,7 @@ uint64_t b200_launch_count(b200_engine *e);
 int b200_quant_table(int power_offset, uint32_t *lo, uint32_t *hi, uint8_t *base);
 /* Profiling aid: accumulate the SM-clock cycles block 0 of the client tail kernel spends in each of its
  * seven phases (load, sum1, avg, sum2, peak, gain, store). out (nullable) receives the totals so far. */
-int b200_debug_tail_profile(b200_engine *e, int enable, long long out[8]);
+int b200_debug_tail_profile(b200_engine *e, int enable, long long out[32]);
 
 #ifdef __cplusplus
 }

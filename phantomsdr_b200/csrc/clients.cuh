@@ -760,368 +760,4 @@ __global__ void __launch_bounds__(kTailThreads) client_tail_kernel(const ClientA
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Software-pipelined tails. Same arithmetic as client_tail_kernel, but the seven phases of a frame run as a
-// frame-skewed pipeline inside one CTA, one __syncthreads per tick:
-//
-//   tick t:  load(t) | sum1(t-1) | avg(t-2) | sum2(t-3) | peak(t-4) | gain(t-5) | store(t-6)
-//
-// The three strictly serial float recurrences each own a warp (lane = client) and therefore overlap one
-// another and all the parallel phases; the per-frame cost drops from the SUM of the phases to the longest
-// one (the 4-op gain recurrence). Tiles are small rings indexed by frame: XE x5, ME x3, Y x2, P x3.
-// cpb = 8 clients per CTA; warps: 0 sum1, 1 sum2, 2 gain, then per client one load/avg warp, one peak warp and
-// one store warp.
-// ------------------------------------------------------------------------------------------------
-constexpr int kPipeCpb = 8;
-constexpr int kPipeWarps = 3 + 3 * kPipeCpb;
-constexpr int kPipeThreads = 32 * kPipeWarps;
-constexpr int kPipeMaxFrames = 64;
-constexpr int kXE = 5, kME = 3, kY = 2, kPR = 3;  // ring depths: distinct slots for every stage that touches a tile in one tick
-
-__host__ __device__ inline size_t tail_pipe_smem(int h, int D) {
-    const size_t pX = tail_pitch(D + h), pH = tail_pitch(h);
-    return sizeof(float) * kPipeCpb * ((kXE + kME) * pX + (kY + kPR + 2) * pH);
-}
-
-template <int KB>
-__global__ void __launch_bounds__(kPipeThreads, 1) client_tail_pipe_kernel(const ClientArrays ca, const ClientLaunch cl) {
-    extern __shared__ __align__(16) float smem_t[];
-    const int h = ca.h, D = ca.D, L = ca.L, NC = ca.NC;
-    const int F = cl.nframes;
-    const int pX = tail_pitch(D + h), pH = tail_pitch(h);
-    float *tX = smem_t;                          // [cpb][kXE][pX]
-    float *tM = tX + kPipeCpb * kXE * pX;        // [cpb][kME][pX]
-    float *tY = tM + kPipeCpb * kME * pX;        // [cpb][kY][pH]
-    float *tP = tY + kPipeCpb * kY * pH;         // [cpb][kPR][pH]
-    float *tS = tP + kPipeCpb * kPR * pH;        // [cpb][2][pH] scratch of the peak warp (the two old AGC chunks)
-    __shared__ int s_slot[kPipeCpb];
-    __shared__ unsigned char s_valid[kPipeCpb][kPipeMaxFrames];
-    __shared__ long long s_t0[kPipeCpb][kPipeMaxFrames + 1];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g0 = blockIdx.x * kPipeCpb;
-    if (tid < kPipeCpb) s_slot[tid] = (g0 + tid < cl.nactive) ? cl.order[g0 + tid] : -1;
-    __syncthreads();
-
-    // ---- prologue: resets, per-frame validity and AGC sample counters ----
-    if (warp >= 3 && warp < 3 + kPipeCpb) {
-        const int ci = warp - 3, slot = s_slot[ci];
-        if (slot >= 0) {
-            const int fl = ca.slots[slot].flags;
-            if (fl & (CF_RESET_ALL | CF_RESET_AGC)) {  // AGC::reset, audioprocessing.cpp:70-74
-                float *ring = ca.agc_ring + (size_t)slot * NC * h;
-                for (int i = lane; i < NC * h; i += 32) ring[i] = 0.f;
-                for (int i = lane; i < NC; i += 32) ca.agc_cmax[(size_t)slot * NC + i] = 0.f;
-            }
-            if (fl & CF_RESET_ALL)
-                for (int i = lane; i < D; i += 32) {
-                    ca.dc_x[(size_t)slot * D + i] = 0.f;
-                    ca.dc_m[(size_t)slot * D + i] = 0.f;
-                }
-            if (lane == 0) {
-                long long t0 = (fl & (CF_RESET_ALL | CF_RESET_AGC)) ? 0 : ca.agc_t0[slot];
-                for (int f = 0; f < F; f++) {
-                    const unsigned char v = ca.valid_a[(size_t)f * ca.max_clients + slot];
-                    s_valid[ci][f] = v;
-                    s_t0[ci][f] = t0;
-                    if (v) t0 += h;
-                }
-                s_t0[ci][F] = t0;
-            }
-        } else if (lane == 0) {
-            for (int f = 0; f < F; f++) s_valid[ci][f] = 0;
-        }
-    }
-    // serial warps: lane = client
-    float carry = 0.f;  // sum1 (warp 0), sum2 (warp 1), gain (warp 2)
-    const int my_slot = (warp < 3 && lane < kPipeCpb) ? s_slot[lane] : -1;
-    if (my_slot >= 0) {
-        const int fl = ca.slots[my_slot].flags;
-        if (warp == 0 && !(fl & CF_RESET_ALL)) carry = ca.dc_sum[2 * my_slot];
-        if (warp == 1 && !(fl & CF_RESET_ALL)) carry = ca.dc_sum[2 * my_slot + 1];
-        if (warp == 2 && !(fl & (CF_RESET_ALL | CF_RESET_AGC))) carry = ca.agc_gain[my_slot];
-    }
-    __syncthreads();
-
-    const float Df = (float)D;
-    constexpr bool kStatic = KB > 0;
-    const int seg = kStatic ? KB : (h + 31) / 32;
-    const int group = (warp - 3) / kPipeCpb;       // 0 load/avg, 1 peak, 2 store (helper warps)
-    const int hci = (warp - 3) % kPipeCpb;         // helper's client
-    const int hslot = (warp >= 3) ? s_slot[hci] : -1;
-
-    for (int t = 0; t < F + 6; t++) {
-        if (warp == 0) {
-            // ---- sum1(t-1): first running sum of the DC blocker, src/utils.h:80-85 ----
-            const int f = t - 1;
-            if (f >= 0 && f < F && my_slot >= 0 && s_valid[lane][f])
-                carry = running_sum_serial(carry, tX + (lane * kXE + f % kXE) * pX, tM + (lane * kME + f % kME) * pX + D, h, D);
-        } else if (warp == 1) {
-            // ---- sum2(t-3) ----
-            const int f = t - 3;
-            if (f >= 0 && f < F && my_slot >= 0 && s_valid[lane][f])
-                carry = running_sum_serial(carry, tM + (lane * kME + f % kME) * pX, tY + (lane * kY + f % kY) * pH, h, D);
-        } else if (warp == 2) {
-            // ---- gain(t-5): attack/release recurrence, audioprocessing.cpp:54-63 ----
-            const int f = t - 5;
-            if (f >= 0 && f < F && my_slot >= 0 && s_valid[lane][f]) {
-                const float att = ca.attack, rel = ca.release;
-                float *Gg = tP + (lane * kPR + f % kPR) * pH;  // desired gain in, gain sequence out
-                float gain = carry;
-                long long first = (long long)L - 1 - s_t0[lane][f];  // outputs stay 0 until the buffer is full
-                if (first < 0) first = 0;
-                if (first > h) first = h;
-                int j = (int)first;
-                // t = gain - desired; both arms are gain - c*t and attack >= release > 0 picks the arm by max()
-                auto step = [&](float d) {
-                    const float tt = __fsub_rn(gain, d);
-                    gain = __fsub_rn(gain, fmaxf(__fmul_rn(att, tt), __fmul_rn(rel, tt)));
-                    return gain;
-                };
-#define G4(DD, dst)              \
-    {                            \
-        float4 r;                \
-        r.x = step(DD.x);        \
-        r.y = step(DD.y);        \
-        r.z = step(DD.z);        \
-        r.w = step(DD.w);        \
-        sts4(dst, r);            \
-    }
-                for (; (j & 3) && j < h; j++) Gg[j] = step(Gg[j]);
-                if (j + 8 <= h) {
-                    float4 d0 = lds4(Gg + j);
-                    for (; j + 8 <= h; j += 8) {
-                        const float4 d1 = lds4(Gg + j + 4);
-                        G4(d0, Gg + j)
-                        if (j + 12 <= h) d0 = lds4(Gg + j + 8);
-                        G4(d1, Gg + j + 4)
-                    }
-                }
-                for (; j + 4 <= h; j += 4) {
-                    const float4 d = lds4(Gg + j);
-                    G4(d, Gg + j)
-                }
-#undef G4
-                for (; j < h; j++) Gg[j] = step(Gg[j]);
-                carry = gain;
-            }
-        } else if (hslot >= 0 && group == 0) {
-            // ---- load(t): audio of frame t into the extended DC row; DC input state carried in shared memory ----
-            {
-                const int f = t;
-                if (f < F) {
-                    float *X = tX + (hci * kXE + f % kXE) * pX;
-                    float st[4];  // D <= 128: the D state values of this lane
-                    const float *prev = (f > 0) ? tX + (hci * kXE + (f - 1) % kXE) * pX + h : nullptr;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int j = lane + 32 * u;
-                        st[u] = (j < D) ? (prev ? prev[j] : ca.dc_x[(size_t)hslot * D + j]) : 0.f;
-                    }
-                    __syncwarp();
-                    if (s_valid[hci][f]) {
-                        const float *a = ca.audio_pre + ((size_t)f * ca.max_clients + hslot) * h;
-                        for (int j = lane; j < h; j += 32) X[D + j] = a[j];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int j = lane + 32 * u;
-                            if (j < D) X[j] = st[u];
-                        }
-                    } else {  // dropped frame: the state passes through unchanged (nobody reads X[0..D) of it)
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int j = lane + 32 * u;
-                            if (j < D) X[h + j] = st[u];
-                        }
-                    }
-                }
-            }
-            // ---- avg(t-2): getAverage() = sum / length; first-stage average state carried likewise ----
-            {
-                const int f = t - 2;
-                if (f >= 0 && f < F) {
-                    float *Mx = tM + (hci * kME + f % kME) * pX;
-                    float st[4];
-                    const float *prev = (f > 0) ? tM + (hci * kME + (f - 1) % kME) * pX + h : nullptr;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int j = lane + 32 * u;
-                        st[u] = (j < D) ? (prev ? prev[j] : ca.dc_m[(size_t)hslot * D + j]) : 0.f;
-                    }
-                    __syncwarp();
-                    if (s_valid[hci][f]) {
-                        for (int j = lane; j < h; j += 32) Mx[D + j] = __fdiv_rn(Mx[D + j], Df);
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int j = lane + 32 * u;
-                            if (j < D) Mx[j] = st[u];
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int j = lane + 32 * u;
-                            if (j < D) Mx[h + j] = st[u];
-                        }
-                    }
-                }
-            }
-        } else if (hslot >= 0 && group == 1) {
-            // ---- peak(t-4): DC output y, window maximum, desired gain; y appended to the AGC ring ----
-            const int f = t - 4;
-            if (f >= 0 && f < F && s_valid[hci][f]) {
-                const float *X = tX + (hci * kXE + f % kXE) * pX;
-                float *Y = tY + (hci * kY + f % kY) * pH;
-                float *Pp = tP + (hci * kPR + f % kPR) * pH;
-                float *R0 = tS + (hci * 2 + 0) * pH, *R1 = tS + (hci * 2 + 1) * pH;
-                const long long tt = s_t0[hci][f];
-                const long long lo0 = tt - L + 1;
-                const long long c0 = floordiv_ll(lo0, h);
-                const int col0 = (int)(lo0 - c0 * h);
-                const long long Fc = tt / h;
-                float *ring = ca.agc_ring + (size_t)hslot * NC * h;
-                float *cmax = ca.agc_cmax + (size_t)hslot * NC;
-                const float *row0 = ring + (size_t)((((c0) % NC) + NC) % NC) * h;
-                const float *row1 = ring + (size_t)((((c0 + 1) % NC) + NC) % NC) * h;
-                float m0 = 0.f, m1 = 0.f;
-                for (long long c = c0 + 1 + lane; c <= Fc - 1; c += 32) {
-                    const float v = cmax[(int)(((c % NC) + NC) % NC)];
-                    m0 = fmaxf(m0, v);
-                    if (c >= c0 + 2) m1 = fmaxf(m1, v);
-                }
-                for (int col = lane; col < h; col += 32) {
-                    R0[col] = row0[col];
-                    R1[col] = row1[col];
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-                    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-                }
-                __syncwarp();
-                // old part of the window: suffix maxima inside the two oldest chunks (lane owns a segment)
-                const int s0 = lane * seg;
-                float run0 = 0.f, run1 = 0.f;
-#pragma unroll
-                for (int u = (kStatic ? KB : seg) - 1; u >= 0; u--) {
-                    const int col = s0 + u;
-                    if (col < h) {
-                        run0 = fmaxf(run0, fabsf(R0[col]));
-                        run1 = fmaxf(run1, fabsf(R1[col]));
-                    }
-                }
-                float in0 = run0, in1 = run1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float a0 = __shfl_down_sync(0xffffffffu, in0, o);
-                    const float a1 = __shfl_down_sync(0xffffffffu, in1, o);
-                    if (lane + o < 32) {
-                        in0 = fmaxf(in0, a0);
-                        in1 = fmaxf(in1, a1);
-                    }
-                }
-                run0 = __shfl_down_sync(0xffffffffu, in0, 1);
-                run1 = __shfl_down_sync(0xffffffffu, in1, 1);
-                if (lane == 31) run0 = run1 = 0.f;
-#pragma unroll
-                for (int u = (kStatic ? KB : seg) - 1; u >= 0; u--) {
-                    const int col = s0 + u;
-                    if (col < h) {
-                        run0 = fmaxf(run0, fabsf(R0[col]));
-                        run1 = fmaxf(run1, fabsf(R1[col]));
-                        const int ja = col - col0, jb = h + col - col0;
-                        if (ja >= 0) Pp[ja] = fmaxf(run0, m0);
-                        if (jb < h) Pp[jb] = fmaxf(run1, m1);
-                    }
-                }
-                __syncwarp();
-                // new part: y = x[delayed] - ma2 (src/utils.h:145-149), running |y| maximum, desired gain
-                float run = 0.f;
-#pragma unroll
-                for (int u = 0; u < (kStatic ? KB : seg); u++) {
-                    const int j = s0 + u;
-                    if (j < h) {
-                        const float y = __fsub_rn(X[j + 1], __fdiv_rn(Y[j], Df));
-                        Y[j] = y;
-                        run = fmaxf(run, fabsf(y));
-                    }
-                }
-                float incl = run;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float other = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl = fmaxf(incl, other);
-                }
-                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = 0.f;
-                run = excl;
-#pragma unroll
-                for (int u = 0; u < (kStatic ? KB : seg); u++) {
-                    const int j = s0 + u;
-                    if (j < h) {
-                        run = fmaxf(run, fabsf(Y[j]));
-                        const float peak = fmaxf(Pp[j], run);
-                        Pp[j] = __fdiv_rn(ca.desired, __fadd_rn(peak, 1e-10f));
-                    }
-                }
-                const float pmax = __shfl_sync(0xffffffffu, incl, 31);
-                __syncwarp();
-                const int row = (int)(Fc % NC);
-                float *dst = ring + (size_t)row * h;
-                for (int j = lane; j < h; j += 32) dst[j] = Y[j];
-                if (lane == 0) cmax[row] = pmax;
-                __syncwarp();
-            }
-        } else if (hslot >= 0 && group == 2) {
-            // ---- store(t-6): delayed sample * gain -> int16 (dsp.cpp:152-165 with mult = 65536/4) ----
-            const int f = t - 6;
-            if (f >= 0 && f < F) {
-                int *pcm = ca.pcm + ((size_t)f * ca.max_clients + hslot) * h;
-                if (!s_valid[hci][f]) {
-                    for (int j = lane; j < h; j += 32) pcm[j] = 0;
-                    if (lane == 0) ca.valid[(size_t)f * ca.max_clients + hslot] = 0;
-                } else {
-                    const float *Gg = tP + (hci * kPR + f % kPR) * pH;
-                    const long long tt = s_t0[hci][f];
-                    const long long lo0 = tt - L + 1;
-                    const long long c0 = floordiv_ll(lo0, h);
-                    const int col0 = (int)(lo0 - c0 * h);
-                    const float *ring = ca.agc_ring + (size_t)hslot * NC * h;
-                    const float *row0 = ring + (size_t)((((c0) % NC) + NC) % NC) * h;
-                    const float *row1 = ring + (size_t)((((c0 + 1) % NC) + NC) % NC) * h;
-                    long long first = (long long)L - 1 - tt;
-                    if (first < 0) first = 0;
-                    for (int j = lane; j < h; j += 32) {
-                        const int pos = col0 + j;
-                        const float cur = (pos < h) ? row0[pos] : row1[pos - h];
-                        const float o = (j < first) ? 0.f : __fmul_rn(cur, Gg[j]);
-                        const float tq = __fadd_rn(__fmul_rn(o, 16384.f), 32768.5f);
-                        int v = __float2int_rz(tq) - 32768;
-                        v = max(min(v, 32767), -32768);
-                        pcm[j] = v;
-                    }
-                    if (lane == 0) ca.valid[(size_t)f * ca.max_clients + hslot] = 1;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    // ---- epilogue: carry the state to the next launch ----
-    if (my_slot >= 0) {
-        if (warp == 0) ca.dc_sum[2 * my_slot] = carry;
-        if (warp == 1) ca.dc_sum[2 * my_slot + 1] = carry;
-        if (warp == 2) {
-            ca.agc_gain[my_slot] = carry;
-            ca.agc_t0[my_slot] = s_t0[lane][F];
-        }
-    }
-    if (hslot >= 0 && group == 0 && F > 0) {
-        const float *X = tX + (hci * kXE + (F - 1) % kXE) * pX + h;
-        const float *Mx = tM + (hci * kME + (F - 1) % kME) * pX + h;
-        for (int j = lane; j < D; j += 32) {
-            ca.dc_x[(size_t)hslot * D + j] = X[j];
-            ca.dc_m[(size_t)hslot * D + j] = Mx[j];
-        }
-    }
-}
-
 }  // namespace b200

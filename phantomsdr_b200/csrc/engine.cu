@@ -16,6 +16,7 @@
 
 #include "../../include/phantomsdr_b200.h"
 #include "clients.cuh"
+#include "clients_tail.cuh"
 #include "fft_fwd.cuh"
 #include "fft_tma.cuh"
 #include "fft_stream.cuh"
@@ -234,6 +235,16 @@ struct b200_engine {
     int *d_order = nullptr;
     int tail_cpb = 32;
     size_t tail_smem = 0;
+    // With banks > 1 the tails of batch k run on their own stream, concurrently with the forward group and the demodulation
+    // of batch k + 1: they are latency-bound (serial recurrences) and occupy few SMs. Audio and PCM are double-buffered.
+    cudaStream_t tstream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_demod[2] = {}, ev_tail[2] = {}, ev_join = nullptr;
+    bool tail_pending[2] = {};
+    int tail_buf = 0;                   // buffer the NEXT client batch uses
+    int last_buf = 0;                   // buffer that holds the results of the last client batch
+    bool use_tail2 = false;             // lane-per-client pipeline (clients_tail.cuh) with its own state layout
+    Tail2State t2{};
+    int *h_tail_err = nullptr;          // pinned mirror of t2.err
     int last_client_frames = 0;
     int demod_fchunk = 1;
     long long *d_prof = nullptr;
@@ -262,6 +273,18 @@ struct b200_engine {
     }
     int8_t *quant_ptr() const { return d_quant + (size_t)cur_bank * batch * pyr_stride; }
     cudaStream_t client_stream() const { return banks > 1 ? cstream : stream; }
+    bool tail_async() const { return use_tail2 && banks > 1 && tstream != nullptr; }
+    cudaStream_t tail_stream() const { return tail_async() ? tstream : client_stream(); }
+    // per-batch client buffers (audio before the tails, validity, PCM) of buffer b
+    ClientArrays client_arrays(int b) const {
+        ClientArrays c = ca;
+        const size_t mc = ca.max_clients, h = ca.h, F = batch;
+        c.audio_pre += (size_t)b * F * mc * h;
+        c.valid_a += (size_t)b * F * mc;
+        c.pcm += (size_t)b * F * mc * h;
+        c.valid += (size_t)b * F * mc;
+        return c;
+    }
 };
 
 namespace {
@@ -587,6 +610,8 @@ int launch_stream(b200_engine *e, const FwdParams &p, const PyrParams &q, int f0
 int stream_check(b200_engine *e) {
     if (e->stream_used && e->h_abort && *e->h_abort)
         return fail(B200_ECUDA, "forward stream kernel: a bounded wait expired (protocol timeout); results of the batch are incomplete");
+    if (e->h_tail_err && *e->h_tail_err)
+        return fail(B200_ECUDA, "client tail pipeline: a bounded wait expired (protocol timeout); results of the batch are incomplete");
     return 0;
 }
 
@@ -946,60 +971,51 @@ std::vector<int> factorize(int n) {
 
 constexpr int kDemodThreads = 256;
 
-int launch_demod(b200_engine *e, const ClientLaunch &cl) {
+int launch_demod(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
     const size_t smem = sizeof(float2) * 2 * e->ca.n * e->demod_fchunk;
     if (cl.nactive == 0) {  // preparation call from clients_create
         CU(cudaFuncSetAttribute(client_demod_kernel<kDemodThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
-    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, e->client_stream()>>>(e->ca, cl);
+    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, e->client_stream()>>>(ca, cl);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
 }
 
-template <int KB> int launch_tail_kb(b200_engine *e, const ClientLaunch &cl) {
+template <int KB> int launch_tail_kb(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
     if (cl.nactive == 0) {  // preparation call from clients_create
         CU(cudaFuncSetAttribute(client_tail_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tail_smem));
         return 0;
     }
     const int blocks = (cl.nactive + cl.cpb - 1) / cl.cpb;
-    client_tail_kernel<KB><<<blocks, kTailThreads, e->tail_smem, e->client_stream()>>>(e->ca, cl);
+    client_tail_kernel<KB><<<blocks, kTailThreads, e->tail_smem, e->tail_stream()>>>(ca, cl);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
 }
-template <int KB> int launch_tail_pipe_kb(b200_engine *e, const ClientLaunch &cl) {
-    const size_t smem = tail_pipe_smem(e->ca.h, e->ca.D);
+int launch_tail2(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
+    const size_t smem = tail2_smem(e->ca.D);
     if (cl.nactive == 0) {  // preparation call from clients_create
-        CU(cudaFuncSetAttribute(client_tail_pipe_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(client_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
-    const int blocks = (cl.nactive + kPipeCpb - 1) / kPipeCpb;
-    client_tail_pipe_kernel<KB><<<blocks, kPipeThreads, smem, e->client_stream()>>>(e->ca, cl);
+    const int groups = (e->ca.max_clients + 31) / 32;
+    client_tail2_kernel<<<groups, kT2Threads, smem, e->tail_stream()>>>(ca, cl, e->t2);
     e->launches++;
     CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_tail_err, e->t2.err, sizeof(int), cudaMemcpyDeviceToHost, e->tail_stream()));
     return 0;
 }
-bool tail_pipe_ok(const b200_engine *e) {
-    // frame-skewed pipeline: DC delay state kept as <= 4 values per lane, tiles must fit, and batches only
-    return e->opt_tail_pipe && e->ca.D <= 128 && tail_pipe_smem(e->ca.h, e->ca.D) <= 200 * 1024 && e->batch <= kPipeMaxFrames;
-}
-int launch_tail(b200_engine *e, const ClientLaunch &cl) {
+int launch_tail(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
+    if (e->use_tail2) return launch_tail2(e, ca, cl);
     const int kb = (e->ca.h + 31) / 32;
-    if (tail_pipe_ok(e) && (cl.nactive == 0 || cl.nframes >= 4)) {
-        int rc;
-        if (kb <= 6) rc = launch_tail_pipe_kb<6>(e, cl);
-        else if (kb <= 9) rc = launch_tail_pipe_kb<9>(e, cl);
-        else rc = launch_tail_pipe_kb<0>(e, cl);
-        if (rc || cl.nactive != 0) return rc;
-    }
-    if (kb <= 2) return launch_tail_kb<2>(e, cl);
-    if (kb <= 4) return launch_tail_kb<4>(e, cl);
-    if (kb <= 6) return launch_tail_kb<6>(e, cl);
-    if (kb <= 9) return launch_tail_kb<9>(e, cl);
-    if (kb <= 12) return launch_tail_kb<12>(e, cl);
-    return launch_tail_kb<0>(e, cl);
+    if (kb <= 2) return launch_tail_kb<2>(e, ca, cl);
+    if (kb <= 4) return launch_tail_kb<4>(e, ca, cl);
+    if (kb <= 6) return launch_tail_kb<6>(e, ca, cl);
+    if (kb <= 9) return launch_tail_kb<9>(e, ca, cl);
+    if (kb <= 12) return launch_tail_kb<12>(e, ca, cl);
+    return launch_tail_kb<0>(e, ca, cl);
 }
 
 int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
@@ -1016,6 +1032,9 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
             if (e->slots[a].l != e->slots[b].l) return e->slots[a].l < e->slots[b].l;
             return e->slots[a].r < e->slots[b].r;
         });
+        if (e->tail_async())  // the previous batch's tails read the reset flags of ITS slot table when they start
+            for (int b = 0; b < 2; b++)
+                if (e->tail_pending[b]) CU(cudaStreamWaitEvent(e->client_stream(), e->ev_tail[b], 0));
         CU(cudaMemcpyAsync(e->ca.slots, e->slots.data(), sizeof(ClientSlot) * e->slots.size(), cudaMemcpyHostToDevice,
                            e->client_stream()));
         if (!e->order.empty())
@@ -1025,16 +1044,25 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
         e->slots_dirty = false;
     }
     e->last_client_frames = nframes;
-    cudaStream_t cs = e->client_stream();
+    cudaStream_t cs = e->client_stream(), ts = e->tail_stream();
+    const bool async_tail = e->tail_async();
+    const int buf = async_tail ? e->tail_buf : 0;
+    const ClientArrays cab = e->client_arrays(buf);
     if (e->banks > 1) {
         // everything enqueued on the forward stream so far (this bank's FFT, and any broadcast the caller
         // put behind it) must land before the clients read the bank
         CU(cudaEventRecord(e->ev_fwd[e->cur_bank], e->stream));
         CU(cudaStreamWaitEvent(cs, e->ev_fwd[e->cur_bank], 0));
     }
-    // closed slots read back as invalid
-    CU(cudaMemsetAsync(e->ca.valid, 0, (size_t)e->ca.max_clients * nframes, cs));
-    if (e->order.empty()) return 0;
+    if (async_tail && e->tail_pending[buf]) {  // the tails of two batches ago still own this audio / PCM buffer
+        CU(cudaStreamWaitEvent(cs, e->ev_tail[buf], 0));
+        e->tail_pending[buf] = false;
+    }
+    e->last_buf = buf;
+    if (e->order.empty()) {
+        CU(cudaMemsetAsync(cab.valid, 0, (size_t)e->ca.max_clients * nframes, cs));  // closed slots read back as invalid
+        return 0;
+    }
     ClientLaunch cl{};
     cl.spec = e->spec_ptr();
     cl.spec_stride = e->spec_stride;
@@ -1047,13 +1075,23 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     cl.cpb = e->tail_cpb;
     cl.fchunk = e->demod_fchunk;
     cl.prof = e->d_prof;
-    int rc = launch_demod(e, cl);
+    int rc = launch_demod(e, cab, cl);
     if (rc) return rc;
-    rc = launch_tail(e, cl);
-    if (rc) return rc;
-    if (e->banks > 1) {
+    if (e->banks > 1) {  // the demodulation is the only reader of the spectrum bank
         CU(cudaEventRecord(e->ev_cli[e->cur_bank], cs));
         e->cli_pending[e->cur_bank] = true;
+    }
+    if (async_tail) {
+        CU(cudaEventRecord(e->ev_demod[buf], cs));
+        CU(cudaStreamWaitEvent(ts, e->ev_demod[buf], 0));
+    }
+    CU(cudaMemsetAsync(cab.valid, 0, (size_t)e->ca.max_clients * nframes, ts));  // closed slots read back as invalid
+    rc = launch_tail(e, cab, cl);
+    if (rc) return rc;
+    if (async_tail) {
+        CU(cudaEventRecord(e->ev_tail[buf], ts));
+        e->tail_pending[buf] = true;
+        e->tail_buf ^= 1;
     }
     // one-shot reset flags have been consumed by this launch
     bool any = false;
@@ -1134,7 +1172,8 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
+    void *dev[] = {e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax, e->t2.err,
+                   e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_qtab, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
                    e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
@@ -1144,6 +1183,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_quant) cudaFreeHost(e->h_quant);
     if (e->h_abort) cudaFreeHost(e->h_abort);
+    if (e->h_tail_err) cudaFreeHost(e->h_tail_err);
     if (e->ev_fwd_done) cudaEventDestroy(e->ev_fwd_done);
     for (int b = 0; b < 4; b++)
         if (e->ev_push[b]) cudaEventDestroy(e->ev_push[b]);
@@ -1154,6 +1194,17 @@ void b200_engine_destroy(b200_engine *e) {
             if (e->ev_cli[b]) cudaEventDestroy(e->ev_cli[b]);
         }
         cudaStreamDestroy(e->cstream);
+    }
+    if (e->tstream) {
+        cudaStreamSynchronize(e->tstream);
+        cudaStreamSynchronize(e->d2h_stream);
+        for (int b = 0; b < 2; b++) {
+            cudaEventDestroy(e->ev_demod[b]);
+            cudaEventDestroy(e->ev_tail[b]);
+        }
+        cudaEventDestroy(e->ev_join);
+        cudaStreamDestroy(e->tstream);
+        cudaStreamDestroy(e->d2h_stream);
     }
     if (e->copy_stream) {
         cudaStreamSynchronize(e->copy_stream);
@@ -1381,6 +1432,8 @@ int b200_sync(b200_engine *e) {
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
     if (e->cstream) CU(cudaStreamSynchronize(e->cstream));
+    if (e->tstream) CU(cudaStreamSynchronize(e->tstream));
+    if (e->d2h_stream) CU(cudaStreamSynchronize(e->d2h_stream));
     return stream_check(e);
 }
 int b200_set_pipeline(b200_engine *e, int banks) {
@@ -1424,6 +1477,9 @@ int b200_join_streams(b200_engine *e) {
     if (e->banks > 1)
         for (int b = 0; b < e->banks; b++)
             if (e->cli_pending[b]) CU(cudaStreamWaitEvent(e->stream, e->ev_cli[b], 0));
+    if (e->tail_async())
+        for (int b = 0; b < 2; b++)
+            if (e->tail_pending[b]) CU(cudaStreamWaitEvent(e->stream, e->ev_tail[b], 0));
     return 0;
 }
 void *b200_stream(b200_engine *e) { return e ? (void *)e->stream : nullptr; }
@@ -1653,12 +1709,36 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     ALLOC0(ca.agc_cmax, sizeof(float) * mc * ca.NC);
     ALLOC0(ca.agc_gain, sizeof(float) * mc);
     ALLOC0(ca.agc_t0, sizeof(long long) * mc);
-    ALLOC0(ca.audio_pre, sizeof(float) * F * mc * h);
-    ALLOC0(ca.valid_a, F * mc);
+    ALLOC0(ca.audio_pre, sizeof(float) * 2 * F * mc * h);  // two batches: see tail_async()
+    ALLOC0(ca.valid_a, 2 * F * mc);
     ALLOC0(ca.pwr, sizeof(float) * F * mc);
-    ALLOC0(ca.pcm, sizeof(int) * F * mc * h);
-    ALLOC0(ca.valid, F * mc);
+    ALLOC0(ca.pcm, sizeof(int) * 2 * F * mc * h);
+    ALLOC0(ca.valid, 2 * F * mc);
     ALLOC0(e->d_order, sizeof(int) * mc);
+    // lane-per-client tail pipeline: state stored [group of 32 slots][...][32]
+    e->use_tail2 = e->opt_tail_pipe && ca.D <= (int)h && ca.L - 1 >= (int)h && tail2_smem(ca.D) <= 200 * 1024;
+    if (e->use_tail2) {
+        Tail2State &t = e->t2;
+        const size_t groups = (mc + 31) / 32;
+        t.NB = (ca.L - 1 + (int)h - 1) / (int)h + 2;
+        t.kb = (ca.L - 1 + (int)h - 1) / (int)h;                    // ceil((L - 1) / h)
+        t.col0 = ((int)h - (ca.L - 1) % (int)h) % (int)h;           // (pos - (L - 1)) mod h for pos a multiple of h
+        t.nsx = ca.D + (kT2Depth + 1) * kT2CH;
+        t.dpow2 = (ca.D & (ca.D - 1)) == 0;
+        t.pcm16 = 0;
+        ALLOC0(t.dcx, sizeof(float) * groups * ca.D * 32);
+        ALLOC0(t.dcm, sizeof(float) * groups * ca.D * 32);
+        ALLOC0(t.sum, sizeof(float) * groups * 2 * 32);
+        ALLOC0(t.gain, sizeof(float) * groups * 32);
+        ALLOC0(t.since, sizeof(int) * groups * 32);
+        ALLOC0(t.blk, sizeof(int) * groups * 32);
+        ALLOC0(t.ring, sizeof(float) * groups * t.NB * h * 32);
+        ALLOC0(t.suf, sizeof(float) * groups * t.NB * h * 32);
+        ALLOC0(t.cmax, sizeof(float) * groups * t.NB * 32);
+        ALLOC0(t.err, sizeof(int));
+        CU(cudaHostAlloc(&e->h_tail_err, sizeof(int), cudaHostAllocDefault));
+        *e->h_tail_err = 0;
+    }
 #undef ALLOC0
     e->slots.assign(mc, ClientSlot{});
     e->mids.assign(mc, 0.0);
@@ -1673,10 +1753,21 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     e->tail_smem = tail_bytes(e->tail_cpb);
     {
         ClientLaunch none{};
-        int rc = launch_demod(e, none);
+        int rc = launch_demod(e, e->ca, none);
         if (rc) return rc;
-        rc = launch_tail(e, none);
+        rc = launch_tail(e, e->ca, none);
         if (rc) return rc;
+        if (e->use_tail2 && !e->tstream) {
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&e->tstream, cudaStreamNonBlocking, hi));  // few, long-running CTAs: schedule them first
+            CU(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; b++) {
+                CU(cudaEventCreateWithFlags(&e->ev_demod[b], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&e->ev_tail[b], cudaEventDisableTiming));
+            }
+            CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        }
     }
     e->have_clients = true;
     e->slots_dirty = true;
@@ -1755,13 +1846,14 @@ int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_o
     if (frame < 0 || frame >= e->batch) return fail(B200_EINVAL, "frame %d outside batch", frame);
     CU(cudaSetDevice(e->device));
     const size_t mc = e->ca.max_clients, h = e->ca.h;
-    cudaStream_t cs = e->client_stream();
-    if (pcm_out)
-        CU(cudaMemcpyAsync(pcm_out, e->ca.pcm + (size_t)frame * mc * h, sizeof(int32_t) * mc * h, cudaMemcpyDeviceToHost, cs));
+    cudaStream_t cs = e->client_stream(), ts = e->tail_stream();
+    const ClientArrays cab = e->client_arrays(e->last_buf);
+    if (pcm_out) CU(cudaMemcpyAsync(pcm_out, cab.pcm + (size_t)frame * mc * h, sizeof(int32_t) * mc * h, cudaMemcpyDeviceToHost, ts));
     if (pwr_out) CU(cudaMemcpyAsync(pwr_out, e->ca.pwr + (size_t)frame * mc, sizeof(float) * mc, cudaMemcpyDeviceToHost, cs));
-    if (valid_out) CU(cudaMemcpyAsync(valid_out, e->ca.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, cs));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, cab.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, ts));
     CU(cudaStreamSynchronize(cs));
-    return 0;
+    if (ts != cs) CU(cudaStreamSynchronize(ts));
+    return stream_check(e);
 }
 
 int b200_clients_execute(b200_engine *e, uint64_t frame_num, int32_t *pcm_out, float *pwr_out, uint8_t *valid_out) {
@@ -1771,15 +1863,15 @@ int b200_clients_execute(b200_engine *e, uint64_t frame_num, int32_t *pcm_out, f
     return b200_clients_fetch(e, 0, pcm_out, pwr_out, valid_out);
 }
 
-void *b200_device_pcm(b200_engine *e) { return e ? e->ca.pcm : nullptr; }
+void *b200_device_pcm(b200_engine *e) { return e ? e->client_arrays(e->last_buf).pcm : nullptr; }
 void *b200_device_pwr(b200_engine *e) { return e ? e->ca.pwr : nullptr; }
-void *b200_device_valid(b200_engine *e) { return e ? e->ca.valid : nullptr; }
+void *b200_device_valid(b200_engine *e) { return e ? e->client_arrays(e->last_buf).valid : nullptr; }
 
 int b200_clients_read_pre_dc(b200_engine *e, float *out) {
     if (!e || !out) return fail(B200_EINVAL, "null argument");
     if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
     CU(cudaSetDevice(e->device));
-    CU(cudaMemcpyAsync(out, e->ca.audio_pre, sizeof(float) * (size_t)e->ca.max_clients * e->ca.h, cudaMemcpyDeviceToHost,
+    CU(cudaMemcpyAsync(out, e->client_arrays(e->last_buf).audio_pre, sizeof(float) * (size_t)e->ca.max_clients * e->ca.h, cudaMemcpyDeviceToHost,
                        e->client_stream()));
     CU(cudaStreamSynchronize(e->client_stream()));
     return 0;
@@ -1906,9 +1998,21 @@ int b200_submit_block(b200_engine *e, const void *const *new_halves, int nframes
         rc = run_clients(e, frame_num0, nframes);
         if (rc) return rc;
         const size_t mc = e->ca.max_clients, h = e->ca.h;
-        if (pcm_out) CU(cudaMemcpyAsync(pcm_out, e->ca.pcm, sizeof(int32_t) * mc * h * nframes, cudaMemcpyDeviceToHost, cs));
+        const ClientArrays cab = e->client_arrays(e->last_buf);
         if (pwr_out) CU(cudaMemcpyAsync(pwr_out, e->ca.pwr, sizeof(float) * mc * nframes, cudaMemcpyDeviceToHost, cs));
-        if (valid_out) CU(cudaMemcpyAsync(valid_out, e->ca.valid, mc * nframes, cudaMemcpyDeviceToHost, cs));
+        if (e->tail_async()) {
+            // PCM and validity leave on their own stream once the tails of THIS block are done, so that the tails of the
+            // next block (other buffer) do not wait for the copy
+            cs = e->d2h_stream;
+            CU(cudaStreamWaitEvent(cs, e->ev_tail[e->last_buf], 0));
+            CU(cudaEventRecord(e->ev_join, e->client_stream()));
+            CU(cudaStreamWaitEvent(cs, e->ev_join, 0));
+        }
+        if (pcm_out) CU(cudaMemcpyAsync(pcm_out, cab.pcm, sizeof(int32_t) * mc * h * nframes, cudaMemcpyDeviceToHost, cs));
+        if (valid_out) CU(cudaMemcpyAsync(valid_out, cab.valid, mc * nframes, cudaMemcpyDeviceToHost, cs));
+        if (e->tail_async()) {  // the buffer is free again only when the copy has read it
+            CU(cudaEventRecord(e->ev_tail[e->last_buf], cs));
+        }
     }
     // block completion = client results on the host and (engine stream) the pyramid on the host
     CU(cudaEventRecord(e->ev_out[slot], e->stream));
@@ -1938,17 +2042,17 @@ int b200_quant_table(int power_offset, uint32_t *lo, uint32_t *hi, uint8_t *base
     return 0;
 }
 
-int b200_debug_tail_profile(b200_engine *e, int enable, long long out[8]) {
+int b200_debug_tail_profile(b200_engine *e, int enable, long long out[32]) {
     if (!e) return fail(B200_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
     if (e->d_prof && out) {
         CU(cudaDeviceSynchronize());
-        CU(cudaMemcpy(out, e->d_prof, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out, e->d_prof, sizeof(long long) * 32, cudaMemcpyDeviceToHost));
     }
     if (enable && !e->d_prof) {
-        CU(cudaMalloc(&e->d_prof, sizeof(long long) * 8));
+        CU(cudaMalloc(&e->d_prof, sizeof(long long) * 32));
     }
-    if (e->d_prof) CU(cudaMemset(e->d_prof, 0, sizeof(long long) * 8));
+    if (e->d_prof) CU(cudaMemset(e->d_prof, 0, sizeof(long long) * 32));
     if (!enable && e->d_prof) {
         cudaFree(e->d_prof);
         e->d_prof = nullptr;
