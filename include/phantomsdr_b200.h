@@ -68,7 +68,7 @@ int b200_device_count(void);
 /* FFT::FFT(size, nthreads, downsample_levels, brightness_offset), src/fft.h:36, src/fft_impl.cpp:63-70.
  * Builds the periodic Hann window on the host exactly as build_hann_window (src/utils/dsp.cpp:6-11)
  * and uploads it; size_log2 = round(log2(size)) + brightness_offset. `size` must be a power of
- * two (2^16..2^20 for c2c, 2^17..2^21 for r2c in this version -> B200_ENOTSUP otherwise).
+ * two (2^16..2^23 for c2c, 2^17..2^23 for r2c: complex transform length 2^16..2^23 -> B200_ENOTSUP otherwise).
  * `nthreads` is accepted and ignored. `device` is the CUDA ordinal. */
 int b200_engine_create(b200_engine **out, size_t size, int nthreads, int downsample_levels, int brightness_offset,
                        int device);
@@ -108,6 +108,14 @@ int b200_load_complex_input(b200_engine *e, const float *a1, const float *a2);
  * selected by B200_OPT_HOST_MIRROR hold the spectrum and the pyramid of the loaded frame. */
 int b200_execute(b200_engine *e);
 
+/* Waterfall cadence. The reference computes the pyramid in every FFT::execute but SENDS it only when
+ * frame_num % skip_num == 0 (src/fft.cpp:33,102-104; skip_num = 6 at 35 MSPS IQ / 2^20). With skip_num > 1 the engine
+ * computes the pyramid - and copies it to the host (b200_execute's mirror, b200_submit_block's pyramid_out rows) - only
+ * for those frames; the spectrum and the clients are unaffected. The engine counts frames itself from 0 like fft_task;
+ * b200_set_frame_number resynchronises the counter (b200_submit_block takes it from frame_num0). Default 1 = every frame. */
+int b200_set_waterfall_cadence(b200_engine *e, int skip_num);
+int b200_set_frame_number(b200_engine *e, uint64_t frame_num);
+
 #define B200_OPT_RELOAD_BOTH 1   /* 0 (default) / 1 */
 #define B200_OPT_HOST_MIRROR 2   /* bitmask: 1 = spectrum, 2 = pyramid; default 3 */
 #define B200_OPT_INPUT_FORMAT 3  /* B200_FMT_*: format of the halves given to b200_load_raw_input */
@@ -130,6 +138,8 @@ int b200_execute(b200_engine *e);
 #define B200_OPT_FWD_SUB_FRAMES 11 /* frames per forward launch group inside a device batch (default: the whole batch) */
 #define B200_OPT_PASS1_ORDER 12  /* tuning: work-item order of the TMA pass 1 (0 default: column tile sticky, frames swept together) */
 #define B200_OPT_PYRAMID_LAG 13  /* B200_OPT_TMA 3: frames between a pass-2 tile and the pyramid blocks that ride on it (default 2) */
+#define B200_OPT_PCM16 18        /* N2: 1 = PCM rows are int16 [frame][slot][n/2] (half the D2H bytes; values identical), 0 (default) = int32
+                                   as AudioEncoder::process takes them (src/audio.h:26-27). Pipelined tail kernel only. */
 #define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */
 #define B200_OPT_STREAM_LAG1 15  /* ... frame slots between pass 1 and pass 2 of a frame in the item order (default 2) */
 #define B200_OPT_STREAM_LAG2 16  /* ... between pass 1 and the quantiser (default 4) */

@@ -24,6 +24,7 @@ OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_STAGE_MASK, OPT_FUSED_PY
 OPT_PACKED_MATH, OPT_FWD_LANES, OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER = 9, 10, 11, 12
 OPT_PYRAMID_LAG = 13
 OPT_STREAM_GRID, OPT_STREAM_LAG1, OPT_STREAM_LAG2, OPT_STREAM_RING = 14, 15, 16, 17
+OPT_PCM16 = 18
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 
@@ -133,6 +134,13 @@ class B200FFT:
 
     def set_option(self, option: int, value: int) -> None:
         check(self.L.b200_set_option(self.h, option, value))
+
+    def set_waterfall_cadence(self, skip_num: int) -> None:
+        """Pyramids only for frames with frame_num % skip_num == 0 (src/fft.cpp:33,102-104)."""
+        check(self.L.b200_set_waterfall_cadence(self.h, skip_num))
+
+    def set_frame_number(self, frame_num: int) -> None:
+        check(self.L.b200_set_frame_number(self.h, frame_num))
 
     # ---- device-resident streaming form ------------------------------------------------------
     def set_hop_ring(self, nhops: int) -> None:

@@ -257,6 +257,14 @@ struct b200_engine {
     long stream_head = -1;  // ring index of the newest resident half
 
     uint64_t launches = 0;
+    // waterfall cadence: pyramids are computed (and copied to the host) only for frames whose number is a
+    // multiple of wf_skip, as the reference SENDS them (src/fft.cpp:33,102-104); 1 = every frame (FFT::execute's behaviour)
+    int wf_skip = 1;
+    int opt_pcm16 = 0;                  // PCM rows as int16 (N2: half the D2H bytes) instead of the encoder API's int32
+    uint64_t fwd_frame = 0;             // number of the first frame of the next forward batch
+    // waterfall slot gather (b200_waterfall_gather): grow-only device / pinned staging
+    void *d_wf_desc = nullptr, *d_wf_out = nullptr, *h_wf_out = nullptr;
+    size_t wf_desc_cap = 0, wf_out_cap = 0;
 
     size_t format_bytes() const {
         switch (in_format) {
@@ -661,7 +669,11 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         p.npeers = 0;
     }
     // 0 none (pyramid kernel re-reads the spectrum), 1 full epilogue in pass 2, 2 |X|^2 plane from pass 2
-    const int fuse = (e->is_real || e->na > 1) ? 0 : (e->opt_fused_pyramid >= 0 ? e->opt_fused_pyramid : (tma_path(e) ? 0 : 2));
+    // waterfall cadence: frames (fwd_frame + f0 + i) % wf_skip == 0 of this range get a pyramid
+    const int wf_skip = std::max(1, e->wf_skip);
+    const int wf_first = (int)((wf_skip - (e->fwd_frame + (uint64_t)f0) % wf_skip) % wf_skip);
+    const int wf_count = wf_first < frames ? (frames - wf_first + wf_skip - 1) / wf_skip : 0;
+    const int fuse = (e->is_real || e->na > 1 || wf_skip > 1) ? 0 : (e->opt_fused_pyramid >= 0 ? e->opt_fused_pyramid : (tma_path(e) ? 0 : 2));
     int base_level = 0;
     while ((1 << base_level) < e->sp2.T) base_level++;
     int8_t *quant = e->quant_ptr() + (size_t)f0 * e->pyr_stride;
@@ -696,11 +708,22 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     q.base_level = fuse == 1 ? base_level : 0;
     q.ntiles = fuse == 2 ? e->sp1.S : (tma ? kS / kTmaT : e->sp1.S / e->sp2.T);
     q.N2 = e->sp2.S;
-    q.npeers = e->is_real ? e->npeers : 0;
+    q.npeers = (e->is_real && e->opt_peer_stores) ? e->npeers : 0;  // (copy-engine mode: b200_push_peers moves the bank)
     q.qtab = (e->opt_packed & 2) ? e->d_qtab : nullptr;
-    for (int i = 0; i < q.npeers; i++) q.peers[i] = e->peers[i] + (size_t)f0 * e->spec_stride;
+    q.frame0 = 0;
+    q.frame_step = 1;
+    q.wf_first = wf_first;
+    q.wf_skip = wf_skip;
+    for (int i = 0; i < q.npeers; i++) {
+        // peer buffers are addressed like the local bank: same frame stride, same bank offset (as the c2c path above)
+        q.peers[i] = e->peers[i] + ((size_t)e->cur_bank * e->batch + f0) * e->spec_stride;
+        for (int j = 0; j < 2; j++) {
+            q.peer_lo[i][j] = e->peer_lo[i][j];
+            q.peer_hi[i][j] = e->peer_hi[i][j];
+        }
+    }
     // opt_tma 3: pass 2 of the TMA path also produces the whole pyramid (FUSE 3), unless a stage is masked out for profiling
-    const bool fused = tma && e->opt_tma == 3 && fuse == 0 && !e->is_real && e->na == 1 && (e->opt_packed & 1) &&
+    const bool fused = tma && e->opt_tma == 3 && fuse == 0 && wf_skip == 1 && !e->is_real && e->na == 1 && (e->opt_packed & 1) &&
                        (e->opt_stage_mask & 6) == 6 && frames <= 64 && e->levels > 0 &&
                        e->opt_lanes <= 1;  // its CTAs wait on one another: never two such grids competing for the SMs
     if (e->na > 1) {
@@ -711,7 +734,7 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         if (rc) return rc;
         if (e->opt_stage_mask & 2) rc = dispatch_pass2(e, p, frames * e->na, 0);
         if (rc) return rc;
-    } else if (stream_path(e) && frames <= 64) {
+    } else if (stream_path(e) && frames <= 64 && wf_skip == 1) {
         // all three stages in one persistent, dataflow-scheduled launch (fft_stream.cuh): Y and the spectrum a quantiser
         // item reads never leave L2. The 1/N normalisation rides on pass 1's window table.
         return launch_stream(e, p, q, f0, frames);
@@ -733,28 +756,42 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     if (e->levels > q.base_level) {
         // 16 entries per thread for the full-resolution inputs, 4 for the small per-tile sums of mode 1
         const int per = (fuse == 1) ? 4 : 16;
-        dim3 grid((unsigned)((e->R >> q.base_level) / (256 * per)), frames);
-        const bool pk = e->opt_packed & 1;
-        if (e->is_real) {
-            if (pk) pyramid_kernel<PYR_R2C, 16, true><<<grid, 256, 0, e->stream>>>(q);
-            else pyramid_kernel<PYR_R2C, 16, false><<<grid, 256, 0, e->stream>>>(q);
-        } else if (fuse == 1) {
-            if (pk) pyramid_kernel<PYR_SCRATCH, 4, true><<<grid, 256, 0, e->stream>>>(q);
-            else pyramid_kernel<PYR_SCRATCH, 4, false><<<grid, 256, 0, e->stream>>>(q);
-        } else if (fuse == 2) {
-            if (pk && q.qtab) pyramid_kernel<PYR_POWER, 16, true, true><<<grid, 256, 0, e->stream>>>(q);
-            else if (pk) pyramid_kernel<PYR_POWER, 16, true><<<grid, 256, 0, e->stream>>>(q);
-            else pyramid_kernel<PYR_POWER, 16, false><<<grid, 256, 0, e->stream>>>(q);
-        } else {
-            if (pk && q.qtab) pyramid_kernel<PYR_SPEC, 16, true, true><<<grid, 256, 0, e->stream>>>(q);
-            else if (pk) pyramid_kernel<PYR_SPEC, 16, true><<<grid, 256, 0, e->stream>>>(q);
-            else pyramid_kernel<PYR_SPEC, 16, false><<<grid, 256, 0, e->stream>>>(q);
+        // r2c: the kernel also does the Hermitian split, so it covers every frame and drops the pyramid of the frames
+        // between two sends itself; c2c: only the send frames are launched
+        int pyr_frames = frames;
+        if (!e->is_real && wf_skip > 1) {
+            q.frame0 = wf_first;
+            q.frame_step = wf_skip;
+            pyr_frames = wf_count;
         }
-        e->launches++;
-        CU(cudaGetLastError());
+        if (pyr_frames > 0) {
+            dim3 grid((unsigned)((e->R >> q.base_level) / (256 * per)), pyr_frames);
+            const bool pk = e->opt_packed & 1;
+            if (e->is_real) {
+                if (pk) pyramid_kernel<PYR_R2C, 16, true><<<grid, 256, 0, e->stream>>>(q);
+                else pyramid_kernel<PYR_R2C, 16, false><<<grid, 256, 0, e->stream>>>(q);
+            } else if (fuse == 1) {
+                if (pk) pyramid_kernel<PYR_SCRATCH, 4, true><<<grid, 256, 0, e->stream>>>(q);
+                else pyramid_kernel<PYR_SCRATCH, 4, false><<<grid, 256, 0, e->stream>>>(q);
+            } else if (fuse == 2) {
+                if (pk && q.qtab) pyramid_kernel<PYR_POWER, 16, true, true><<<grid, 256, 0, e->stream>>>(q);
+                else if (pk) pyramid_kernel<PYR_POWER, 16, true><<<grid, 256, 0, e->stream>>>(q);
+                else pyramid_kernel<PYR_POWER, 16, false><<<grid, 256, 0, e->stream>>>(q);
+            } else {
+                if (pk && q.qtab) pyramid_kernel<PYR_SPEC, 16, true, true><<<grid, 256, 0, e->stream>>>(q);
+                else if (pk) pyramid_kernel<PYR_SPEC, 16, true><<<grid, 256, 0, e->stream>>>(q);
+                else pyramid_kernel<PYR_SPEC, 16, false><<<grid, 256, 0, e->stream>>>(q);
+            }
+            e->launches++;
+            CU(cudaGetLastError());
+        }
         const int levels_done = (per == 16 ? 4 : 2) + 9;
-        if (e->levels - q.base_level > levels_done) {
-            pyramid_tail_kernel<<<frames, 512, 0, e->stream>>>(q, q.base_level, levels_done);
+        if (e->levels - q.base_level > levels_done && wf_count > 0) {
+            if (wf_skip > 1) {  // (r2c included: only the send frames left sums behind)
+                q.frame0 = wf_first;
+                q.frame_step = wf_skip;
+            }
+            pyramid_tail_kernel<<<wf_skip > 1 ? wf_count : frames, 512, 0, e->stream>>>(q, q.base_level, levels_done);
             e->launches++;
             CU(cudaGetLastError());
         }
@@ -766,7 +803,14 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
 // into sub-batches of opt_sub_frames frames that alternate over the lane streams: every sub-batch's intermediates
 // (Y, |X|^2) live in its lane's small scratch slots, which are rewritten while still resident in L2 (no DRAM round
 // trip), and the lanes fill each other's launch gaps and partial waves.
+int run_forward_batch(b200_engine *e, long hop0, int frames);
+// the frame counter that drives the waterfall cadence advances with every forward batch
 int run_forward(b200_engine *e, long hop0, int frames) {
+    int rc = run_forward_batch(e, hop0, frames);
+    if (!rc) e->fwd_frame += (uint64_t)frames;
+    return rc;
+}
+int run_forward_batch(b200_engine *e, long hop0, int frames) {
     {
         int rc0 = bank_acquire(e);
         if (rc0) return rc0;
@@ -1104,12 +1148,13 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     return 0;
 }
 
-__global__ void waterfall_gather_kernel(const int8_t *quant, const size_t *src_off, const int *len, const size_t *dst_off,
-                                        int8_t *out) {
-    const int c = blockIdx.x;
-    const int8_t *s = quant + src_off[c];
-    int8_t *d = out + dst_off[c];
-    for (int i = threadIdx.x; i < len[c]; i += blockDim.x) d[i] = s[i];
+struct WfDesc { size_t src, dst; long long len; };
+// N x WaterfallClient::send_waterfall (src/waterfall.cpp:44-51): client c's row q_level[l .. r) -> its place in one buffer
+__global__ void waterfall_gather_kernel(const int8_t *quant, const WfDesc *desc, int8_t *out) {
+    const WfDesc d = desc[blockIdx.x];
+    const int8_t *s = quant + d.src;
+    int8_t *o = out + d.dst;
+    for (long long i = threadIdx.x; i < d.len; i += blockDim.x) o[i] = s[i];
 }
 
 }  // namespace
@@ -1183,6 +1228,9 @@ void b200_engine_destroy(b200_engine *e) {
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_quant) cudaFreeHost(e->h_quant);
     if (e->h_abort) cudaFreeHost(e->h_abort);
+    if (e->d_wf_desc) cudaFree(e->d_wf_desc);
+    if (e->d_wf_out) cudaFree(e->d_wf_out);
+    if (e->h_wf_out) cudaFreeHost(e->h_wf_out);
     if (e->h_tail_err) cudaFreeHost(e->h_tail_err);
     if (e->ev_fwd_done) cudaEventDestroy(e->ev_fwd_done);
     for (int b = 0; b < 4; b++)
@@ -1343,6 +1391,11 @@ int b200_set_option(b200_engine *e, int option, int value) {
         if (value < 1 || value > 64) return fail(B200_EINVAL, "sub-batch frames must be 1..64");
         e->opt_sub_frames = value;
         return 0;
+    case B200_OPT_PCM16:
+        if (e->have_clients && !e->use_tail2) return fail(B200_ENOTSUP, "int16 PCM needs the pipelined tail kernel");
+        e->opt_pcm16 = value ? 1 : 0;
+        e->t2.pcm16 = e->opt_pcm16;
+        return 0;
     case B200_OPT_STREAM_GRID:
         if (value < 0 || value > 1024) return fail(B200_EINVAL, "stream grid must be 0 (one CTA per SM) .. 1024");
         e->opt_stream_grid = value;
@@ -1376,16 +1429,29 @@ int b200_execute(b200_engine *e) {
     if (!e->planned) return fail(B200_ESTATE, "execute before plan");
     if (e->frame_hop0 < 0) return fail(B200_ESTATE, "execute before load_*_input");
     CU(cudaSetDevice(e->device));
+    const bool send_frame = e->fwd_frame % (uint64_t)std::max(1, e->wf_skip) == 0;
     int rc = run_forward(e, e->frame_hop0, 1);
     if (rc) return rc;
     if (e->opt_mirror & 1) {
         const size_t bins = e->is_real ? e->size / 2 + 1 : e->size + e->additional;
         CU(cudaMemcpyAsync(e->h_out, e->spec_ptr(), sizeof(float2) * bins, cudaMemcpyDeviceToHost, e->stream));
     }
-    if (e->opt_mirror & 2)
+    if ((e->opt_mirror & 2) && send_frame)
         CU(cudaMemcpyAsync(e->h_quant, e->quant_ptr(), e->pyr_bytes, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return stream_check(e);
+}
+
+int b200_set_waterfall_cadence(b200_engine *e, int skip_num) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (skip_num < 1) return fail(B200_EINVAL, "skip_num must be >= 1 (src/fft.cpp:33)");
+    e->wf_skip = skip_num;
+    return 0;
+}
+int b200_set_frame_number(b200_engine *e, uint64_t frame_num) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    e->fwd_frame = frame_num;
+    return 0;
 }
 
 void *b200_device_spectrum(b200_engine *e) { return e ? e->spec_ptr() : nullptr; }
@@ -1725,7 +1791,7 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
         t.col0 = ((int)h - (ca.L - 1) % (int)h) % (int)h;           // (pos - (L - 1)) mod h for pos a multiple of h
         t.nsx = ca.D + (kT2Depth + 1) * kT2CH;
         t.dpow2 = (ca.D & (ca.D - 1)) == 0;
-        t.pcm16 = 0;
+        t.pcm16 = e->opt_pcm16;
         ALLOC0(t.dcx, sizeof(float) * groups * ca.D * 32);
         ALLOC0(t.dcm, sizeof(float) * groups * ca.D * 32);
         ALLOC0(t.sum, sizeof(float) * groups * 2 * 32);
@@ -1848,7 +1914,9 @@ int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_o
     const size_t mc = e->ca.max_clients, h = e->ca.h;
     cudaStream_t cs = e->client_stream(), ts = e->tail_stream();
     const ClientArrays cab = e->client_arrays(e->last_buf);
-    if (pcm_out) CU(cudaMemcpyAsync(pcm_out, cab.pcm + (size_t)frame * mc * h, sizeof(int32_t) * mc * h, cudaMemcpyDeviceToHost, ts));
+    const size_t pb = e->opt_pcm16 ? sizeof(int16_t) : sizeof(int32_t);  // bytes per PCM sample
+    if (pcm_out)
+        CU(cudaMemcpyAsync(pcm_out, reinterpret_cast<const char *>(cab.pcm) + (size_t)frame * mc * h * pb, pb * mc * h, cudaMemcpyDeviceToHost, ts));
     if (pwr_out) CU(cudaMemcpyAsync(pwr_out, e->ca.pwr + (size_t)frame * mc, sizeof(float) * mc, cudaMemcpyDeviceToHost, cs));
     if (valid_out) CU(cudaMemcpyAsync(valid_out, cab.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, ts));
     CU(cudaStreamSynchronize(cs));
@@ -1902,29 +1970,39 @@ int b200_waterfall_gather(b200_engine *e, int nclients, const int *level, const 
         dst[i] = out_offsets[i];
         total = std::max(total, dst[i] + (size_t)len[i]);
     }
-    size_t *d_src = nullptr, *d_dst = nullptr;
-    int *d_len = nullptr;
-    int8_t *d_out = nullptr;
-    std::vector<int8_t> staged(std::max<size_t>(total, 1));
-    CU(cudaMalloc(&d_src, sizeof(size_t) * nclients));
-    CU(cudaMalloc(&d_dst, sizeof(size_t) * nclients));
-    CU(cudaMalloc(&d_len, sizeof(int) * nclients));
-    CU(cudaMalloc(&d_out, staged.size()));
-    CU(cudaMemcpyAsync(d_src, src.data(), sizeof(size_t) * nclients, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(d_dst, dst.data(), sizeof(size_t) * nclients, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(d_len, len.data(), sizeof(int) * nclients, cudaMemcpyHostToDevice, e->stream));
-    waterfall_gather_kernel<<<nclients, 256, 0, e->stream>>>(e->quant_ptr(), d_src, d_len, d_dst, d_out);
+    // one descriptor table up, one kernel, one copy down; device and pinned staging buffers only ever grow
+    typedef WfDesc Desc;
+    std::vector<Desc> desc(nclients);
+    for (int i = 0; i < nclients; i++) desc[i] = {src[i], dst[i], (long long)len[i]};
+    const size_t out_bytes = std::max<size_t>(total, 1);
+    if (e->wf_desc_cap < (size_t)nclients) {
+        if (e->d_wf_desc) cudaFree(e->d_wf_desc);
+        e->d_wf_desc = nullptr;
+        e->wf_desc_cap = 0;
+        const size_t cap = std::max<size_t>(256, (size_t)nclients * 2);
+        CU(cudaMalloc(&e->d_wf_desc, sizeof(Desc) * cap));
+        e->wf_desc_cap = cap;
+    }
+    if (e->wf_out_cap < out_bytes) {
+        if (e->d_wf_out) cudaFree(e->d_wf_out);
+        if (e->h_wf_out) cudaFreeHost(e->h_wf_out);
+        e->d_wf_out = e->h_wf_out = nullptr;
+        e->wf_out_cap = 0;
+        const size_t cap = std::max<size_t>(1 << 20, out_bytes * 2);
+        CU(cudaMalloc(&e->d_wf_out, cap));
+        CU(cudaHostAlloc(&e->h_wf_out, cap, cudaHostAllocDefault));
+        e->wf_out_cap = cap;
+    }
+    CU(cudaMemcpyAsync(e->d_wf_desc, desc.data(), sizeof(Desc) * nclients, cudaMemcpyHostToDevice, e->stream));
+    waterfall_gather_kernel<<<nclients, 256, 0, e->stream>>>(e->quant_ptr(), reinterpret_cast<const WfDesc *>(e->d_wf_desc),
+                                                             reinterpret_cast<int8_t *>(e->d_wf_out));
     e->launches++;
-    cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess) err = cudaMemcpyAsync(staged.data(), d_out, staged.size(), cudaMemcpyDeviceToHost, e->stream);
-    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    cudaFree(d_src);
-    cudaFree(d_dst);
-    cudaFree(d_len);
-    cudaFree(d_out);
-    if (err != cudaSuccess) return fail(B200_ECUDA, "waterfall gather failed: %s", cudaGetErrorString(err));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->h_wf_out, e->d_wf_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const int8_t *staged_p = reinterpret_cast<const int8_t *>(e->h_wf_out);
     // only the clients' own byte ranges of `out` are touched
-    for (int i = 0; i < nclients; i++) memcpy(out + dst[i], staged.data() + dst[i], (size_t)len[i]);
+    for (int i = 0; i < nclients; i++) memcpy(out + dst[i], staged_p + dst[i], (size_t)len[i]);
     return 0;
 }
 
@@ -1985,13 +2063,20 @@ int b200_submit_block(b200_engine *e, const void *const *new_halves, int nframes
     // forward on the engine stream
     e->cur_bank = slot % e->banks;
     CU(cudaStreamWaitEvent(e->stream, e->ev_in[slot], 0));
+    e->fwd_frame = frame_num0;
     int rc = run_forward(e, hop0, nframes);
     if (rc) return rc;
     CU(cudaEventRecord(e->ev_ring_free[slot], e->stream));
     if (pyramid_out) {
-        // rows of the batch are pyr_stride apart on the device, pyr_bytes apart for the caller
-        CU(cudaMemcpy2DAsync(pyramid_out, e->pyr_bytes, e->quant_ptr(), e->pyr_stride, e->pyr_bytes, nframes,
-                             cudaMemcpyDeviceToHost, e->stream));
+        // rows of the batch are pyr_stride apart on the device, pyr_bytes apart for the caller; with a waterfall cadence only
+        // the rows of the send frames (frame number a multiple of wf_skip) are produced and copied, the others stay untouched
+        const int skip = std::max(1, e->wf_skip);
+        const int first = (int)((skip - frame_num0 % skip) % skip);
+        const int count = first < nframes ? (nframes - first + skip - 1) / skip : 0;
+        if (count > 0)
+            CU(cudaMemcpy2DAsync(pyramid_out + (size_t)first * e->pyr_bytes, (size_t)skip * e->pyr_bytes,
+                                 e->quant_ptr() + (size_t)first * e->pyr_stride, (size_t)skip * e->pyr_stride, e->pyr_bytes, count,
+                                 cudaMemcpyDeviceToHost, e->stream));
     }
     cudaStream_t cs = e->client_stream();
     if (e->have_clients) {
@@ -2008,7 +2093,8 @@ int b200_submit_block(b200_engine *e, const void *const *new_halves, int nframes
             CU(cudaEventRecord(e->ev_join, e->client_stream()));
             CU(cudaStreamWaitEvent(cs, e->ev_join, 0));
         }
-        if (pcm_out) CU(cudaMemcpyAsync(pcm_out, cab.pcm, sizeof(int32_t) * mc * h * nframes, cudaMemcpyDeviceToHost, cs));
+        if (pcm_out)
+            CU(cudaMemcpyAsync(pcm_out, cab.pcm, (e->opt_pcm16 ? sizeof(int16_t) : sizeof(int32_t)) * mc * h * nframes, cudaMemcpyDeviceToHost, cs));
         if (valid_out) CU(cudaMemcpyAsync(valid_out, cab.valid, mc * nframes, cudaMemcpyDeviceToHost, cs));
         if (e->tail_async()) {  // the buffer is free again only when the copy has read it
             CU(cudaEventRecord(e->ev_tail[e->last_buf], cs));

@@ -492,6 +492,9 @@ struct PyrParams {
     int ntiles, N2;
     int npeers;
     float2 *peers[kMaxPeers];
+    unsigned peer_lo[kMaxPeers][2], peer_hi[kMaxPeers][2];  // PYR_R2C: bins each peer needs (two half-open ranges), as FwdParams
+    int frame0, frame_step;  // the launch covers frames frame0, frame0 + frame_step, ... (blockIdx.y-th of them)
+    int wf_first, wf_skip;   // PYR_R2C (every frame is split): only frames wf_first, wf_first + wf_skip, ... get a pyramid
     const uint2 *qtab;       // optional [3][2048] quantiser tables of levels 0..2 (see quantize_table), or nullptr
 };
 
@@ -634,12 +637,16 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
                 // divided, src/fft_impl.cpp:152-154)
                 const float2 ny = make_float2(a.x - a.y, 0.f);
                 spec[R] = ny;
-                for (int pe = 0; pe < p.npeers; pe++) (p.peers[pe] + (size_t)frame * p.spec_stride)[R] = ny;
+                for (int pe = 0; pe < p.npeers; pe++)
+                    if ((R >= p.peer_lo[pe][0] && R < p.peer_hi[pe][0]) || (R >= p.peer_lo[pe][1] && R < p.peer_hi[pe][1]))
+                        (p.peers[pe] + (size_t)frame * p.spec_stride)[R] = ny;
             }
             x.x *= p.scale;
             x.y *= p.scale;
             spec[k] = x;
-            for (int pe = 0; pe < p.npeers; pe++) (p.peers[pe] + (size_t)frame * p.spec_stride)[k] = x;
+            for (int pe = 0; pe < p.npeers; pe++)
+                if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1]))
+                    (p.peers[pe] + (size_t)frame * p.spec_stride)[k] = x;
             pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
         }
     } else if constexpr (MODE == PYR_POWER) {
@@ -665,19 +672,23 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
             pw[i] = scr[tile * p.N2 + d2];
         }
     }
+    if constexpr (MODE == PYR_R2C) {
+        // waterfall cadence (src/fft.cpp:33,102-104): the split above is needed every frame, the pyramid only on send frames
+        if (p.wf_skip > 1 && (frame < p.wf_first || (frame - p.wf_first) % p.wf_skip != 0)) return;
+    }
     pyramid_tree<PER, PK, TB>(p, frame, blk, tid, pw, B, warp_sum_s, sync);
 }
 
 template <int MODE, int PER, bool PK, bool TB = false> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
     __shared__ float warp_sum_s[8];
-    pyramid_block<MODE, PER, PK, false, TB>(p, blockIdx.y, blockIdx.x, threadIdx.x, warp_sum_s, CtaSync{});
+    pyramid_block<MODE, PER, PK, false, TB>(p, p.frame0 + (int)blockIdx.y * p.frame_step, blockIdx.x, threadIdx.x, warp_sum_s, CtaSync{});
 }
 
 // more than ten levels above the base (only for very deep pyramids): one block per frame, pairwise tree over
 // the sums left in ptop. Tiny.
 __global__ void pyramid_tail_kernel(const PyrParams p, int base_level, int levels_done) {
     // levels_done = relative levels already produced by pyramid_kernel (log2(PER) + 9); ptop holds the sums of the last one
-    const int frame = blockIdx.x;
+    const int frame = p.frame0 + (int)blockIdx.x * p.frame_step;
     const size_t R = (size_t)1 << p.log2R;
     const int first = base_level + levels_done;
     size_t n = R >> (first - 1);
