@@ -12,9 +12,12 @@ client. `value` = IQ samples all ranks processed / device time (CUDA events, max
 `e2e` = the same frames through the reference-facing C-ABI calls with HOST buffers
 (b200_load_complex_input -> b200_execute -> b200_clients_execute), host<->device copies inside.
 
-N > 1 (torchrun): rank 0 ingests and computes each spectrum batch, one NCCL broadcast over NVLink
-delivers it to every rank, every rank demodulates its own 1024 clients (weak scaling: per-GPU
-client load fixed; every rank consumes every frame).
+N > 1 (torchrun): rank 0 ingests and computes each spectrum batch, one exchange step over NVLink delivers it
+to every rank, every rank demodulates its own 1024 clients of the whole stream (weak scaling: per-GPU client
+load fixed). `value` = ingest rate x client shards (= ingest x clients_total / 1024): the stream rate the job
+sustains per 1024-client shard, summed over the N shards; `ingest_msps` is the rate of the ONE ingested
+stream. The same run also times the other exchange modes and a strong-scaling leg (1024 clients in total) and
+reports them under "mgpu". --impl reference uses the same definition on the same client total.
 
 --impl reference : the reference's CPU path (oracle port; FFT by MKL through torch.fft as the
 FFTW substitute) on the host cores, same config/metric, bounded sample per step.
@@ -38,6 +41,9 @@ from phantomsdr_b200 import SpectrumConfig, USB, LSB, AM, FM  # noqa: E402
 from phantomsdr_b200.synth import make_clients  # noqa: E402
 
 METRIC = "IQ MSamples/s ingested @ 1024 demod clients"
+VALUE_DEF = ("ingest rate (frames/s x new samples per frame) x clients_total / clients_per_gpu: at N = 1 the ingest rate; at N > 1 every "
+             "rank demodulates the whole ingested stream for its own shard of clients_per_gpu clients, so the job sustains that "
+             "stream rate once per shard (weak scaling of the client load); ingest_msps is the single stream's rate")
 UNIT = "MS/s"
 
 
@@ -46,7 +52,14 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cufft"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg1", "cfg2", "cfg3"],
+                    help="BASELINE.json configs: cfg1 = [0] rtlsdr 3.2 MSPS u8 IQ, 2^17, 1 USB + waterfall; cfg2 = [1] 35 MSPS IQ, 2^20 "
+                         "(the metric's configuration, at 1024 clients); cfg3 = [2] 70 MSPS real, 2^21, 256 FM + waterfall")
+    ap.add_argument("--waterfall-skip", type=int, default=1,
+                    help="waterfall cadence (SURVEY 8f N3): pyramids only every skip-th frame; 0 = the reference's skip_num")
+    ap.add_argument("--pcm16", action="store_true", help="int16 PCM hand-off (SURVEY 8f N2) in the e2e path")
+    ap.add_argument("--no-mgpu-extras", action="store_true", help="N>1: only the default exchange mode, no strong-scaling leg")
     ap.add_argument("--fft-log2", type=int, default=20)
     ap.add_argument("--sps", type=int, default=35_000_000)
     ap.add_argument("--real", action="store_true", help="r2c input (cfg 3 shape)")
@@ -67,15 +80,30 @@ def parse_args():
                          "straight into that rank's memory over NVLink (peer stores fused into the kernel, flags instead of a "
                          "collective). scatter-dma (default, fastest measured: 194 vs 130 vs 129 GS/s at N=8): same partition "
                          "and flags, the sub-bands pushed by the copy engines so the ingest rank's SMs never wait on NVLink")
-    return ap.parse_args()
+    args = ap.parse_args()
+    explicit = {a.split("=")[0] for a in sys.argv[1:] if a.startswith("--")}
+    if args.config == "cfg1":
+        if "--fft-log2" not in explicit: args.fft_log2 = 17
+        if "--sps" not in explicit: args.sps = 3_200_000
+        if "--clients" not in explicit: args.clients = 1
+        args.modes = (USB,)
+    elif args.config == "cfg3":
+        if "--fft-log2" not in explicit: args.fft_log2 = 21
+        if "--sps" not in explicit: args.sps = 70_000_000
+        if "--clients" not in explicit: args.clients = 256
+        args.real = True
+        args.modes = (FM,)
+    else:
+        args.modes = (AM, USB, LSB)
+    return args
 
 
 def make_cfg(args) -> SpectrumConfig:
     return SpectrumConfig(sps=args.sps, fft_size=1 << args.fft_log2, is_real=args.real)
 
 
-def client_table(cfg, count, rank=0):
-    return make_clients(cfg, count, seed=0x5EED + 1 + 1000 * rank, modes=(AM, USB, LSB))
+def client_table(cfg, count, rank=0, modes=(AM, USB, LSB)):
+    return make_clients(cfg, count, seed=0x5EED + 1 + 1000 * rank, modes=modes)
 
 
 def algorithmic_bytes_per_frame(cfg) -> int:
@@ -188,23 +216,24 @@ def fill_ring(torch, ring_t, cfg, seed):
 # ------------------------------------------------------------------------------------------------
 # reference / CPU baseline: the oracle port of the reference FFTW path on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(cfg, nclients, frames, warm=1):
+def cpu_reference_run(cfg, nclients, frames, warm=1, modes=(AM, USB, LSB), fft_threads=0):
     """Times `frames` frames of the reference CPU path. FFT provider: MKL through torch.fft (the
-    FFTW substitute); window/quantiser/pyramid/clients: oracle/ (OpenMP over all
-    host cores, like fft_impl.cpp:32,53 and the asio pool). Returns (frames/s, info dict)."""
+    FFTW substitute) on `fft_threads` threads (0 = all host cores; 1 = the reference's default,
+    src/spectrumserver.cpp:39); window/quantiser/pyramid/clients: oracle/ (OpenMP over all host cores, like
+    fft_impl.cpp:32,53 and the asio pool). Returns (frames/s, info dict with the forward / clients split)."""
     import torch
 
     import oracle
 
     oracle.build()
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(fft_threads or cores)
     N = cfg.fft_size
     orc = oracle.OracleFFT(N, cfg.downsample_levels, cfg.brightness_offset)
     n = cfg.audio_fft_size
     orc.set_output_additional_size(n)
     orc.plan_r2c() if cfg.is_real else orc.plan_c2c()
-    specs = client_table(cfg, nclients)
+    specs = client_table(cfg, nclients, modes=modes)
     clients = []
     for c in specs:
         o = oracle.OracleClient(cfg.is_real, n, cfg.audio_sps, cfg.fft_result_size)
@@ -216,8 +245,10 @@ def cpu_reference_run(cfg, nclients, frames, warm=1):
     out = orc.outbuf
     inb = orc.inbuf
     nfl = N + 2 if cfg.is_real else 2 * N
+    t_fwd = [0.0]
 
     def one(frame):
+        t0 = time.perf_counter()
         a1, a2 = hops[frame % 4], hops[(frame + 1) % 4]
         if cfg.is_real:
             orc.load_real_input(a1, a2)
@@ -228,17 +259,23 @@ def cpu_reference_run(cfg, nclients, frames, warm=1):
         out[:nfl] = torch.view_as_real(X).reshape(-1).numpy()
         orc.quantize()
         orc.wrap_copy(n)
+        t_fwd[0] += time.perf_counter() - t0
         oracle.clients_send_audio(clients, out, N, cfg.is_real, frame)
 
     for f in range(warm):
         one(f)
+    t_fwd[0] = 0.0
     t0 = time.perf_counter()
     for f in range(frames):
         one(warm + f)
     dt = time.perf_counter() - t0
+    torch.set_num_threads(cores)
     return frames / dt, {"cores": cores, "kind": "port",
                          "sample": f"{frames} frames of the same workload ({nclients} clients); FFT = MKL via torch.fft "
-                                   f"(FFTW substitute), rest = oracle/ C port with OpenMP on {cores} threads"}
+                                   f"(FFTW substitute) on {fft_threads or cores} thread(s), rest = oracle/ C port with OpenMP on "
+                                   f"{cores} threads",
+                         "split_ms_per_frame": {"forward_and_waterfall": 1e3 * t_fwd[0] / frames,
+                                                "clients": 1e3 * (dt - t_fwd[0]) / frames}}
 
 
 def run_reference(args):
@@ -246,34 +283,80 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = make_cfg(args)
+    total_clients = args.clients * max(1, args.gpus)  # the same client total as the b200 arm serves at this N
     # bounded sample per step so that steps+warmup finish within minutes
-    probe_fps, info = cpu_reference_run(cfg, args.clients, frames=3, warm=1)
+    probe_fps, info = cpu_reference_run(cfg, total_clients, frames=3, warm=1, modes=args.modes)
     budget_s = 120.0
     per_step = max(1, int(min(args.ring, budget_s * probe_fps / max(1, args.steps + args.warmup))))
     t_all = []
     for s in range(args.warmup + args.steps):
-        fps, info = cpu_reference_run(cfg, args.clients, frames=per_step, warm=0)
+        fps, info = cpu_reference_run(cfg, total_clients, frames=per_step, warm=0, modes=args.modes)
         if s >= args.warmup:
             t_all.append(per_step / fps)
     ms = 1e3 * float(np.mean(t_all))
-    value = per_step * cfg.hop_samples / (ms * 1e-3) / 1e6
+    ingest = per_step * cfg.hop_samples / (ms * 1e-3) / 1e6
+    value = ingest * max(1, args.gpus)  # VALUE_DEF: ingest x clients_total / clients_per_gpu
     info["sample"] = f"each step = {per_step} frames; " + info["sample"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg, args, 1),
+        "config": workload_config(cfg, args, max(1, args.gpus)),
         "cpu_baseline": {"value": value, "unit": UNIT, **info},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "ingest_msps": ingest,
     }
     print(json.dumps(line), flush=True)
+
+
+def cufft_yardstick(torch, cfg, frames, reps=10):
+    """Bare cuFFT (through torch.fft) on the same box: `frames` batched transforms of the config's size, device-resident,
+    no window, no normalisation, no display shift, no waterfall. The yardstick the reference's own GPU backend is built on
+    (src/fft_cuda.cu:42,58,133-142); never linked into the product. Returns microseconds per frame."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if cfg.is_real:
+        x = torch.randn(frames, cfg.fft_size, device=dev, dtype=torch.float32)
+        fn = lambda: torch.fft.rfft(x)  # noqa: E731
+    else:
+        x = torch.randn(frames, cfg.fft_size, 2, device=dev, dtype=torch.float32)
+        xc = torch.view_as_complex(x)
+        fn = lambda: torch.fft.fft(xc)  # noqa: E731
+    for _ in range(3):
+        y = fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        y = fn()
+    b.record()
+    torch.cuda.synchronize()
+    del y
+    return a.elapsed_time(b) * 1e3 / (reps * frames)
+
+
+def run_cufft(args):
+    import torch
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    cfg = make_cfg(args)
+    us = cufft_yardstick(torch, cfg, args.batch)
+    bytes_frame = (4 * cfg.fft_size + 8 * (cfg.fft_size // 2 + 1)) if cfg.is_real else 16 * cfg.fft_size
+    print(json.dumps({"impl": "cufft", "what": f"torch.fft ({'R2C' if cfg.is_real else 'C2C'} 2^{args.fft_log2}, batch {args.batch}, "
+                      "out of place, device-resident): the bare library transform, no window / shift / normalisation / waterfall",
+                      "us_per_frame": us, "input_plus_output_GBps": bytes_frame / us / 1e3,
+                      "msps": cfg.hop_samples / us}), flush=True)
 
 
 def workload_config(cfg, args, world):
     return {
         "workload": f"{cfg.sps / 1e6:g} MSPS {'real' if cfg.is_real else 'complex-IQ'} synthetic, 2^{args.fft_log2} FFT, "
-                    f"{args.clients} clients/GPU mixed AM/USB/LSB (BASELINE.json configs[1] at the metric's client count)",
+                    f"{args.clients} clients/GPU {'/'.join({USB: 'USB', LSB: 'LSB', AM: 'AM', FM: 'FM'}[m] for m in args.modes)} "
+                    + {"cfg1": "(BASELINE.json configs[0] shape)", "cfg2": "(BASELINE.json configs[1] at the metric's client count)",
+                       "cfg3": "(BASELINE.json configs[2])"}[args.config],
+        "value_definition": VALUE_DEF,
+        "waterfall_every_n_frames": args.waterfall_skip if args.waterfall_skip > 0 else cfg.skip_num,
         "fft_size": cfg.fft_size, "audio_fft_size": cfg.audio_fft_size, "downsample_levels": cfg.downsample_levels,
         "clients_per_gpu": args.clients, "clients_total": args.clients * world,
         "frames_per_step": args.ring, "frames_per_launch": args.batch, "pipeline_banks": args.banks,
@@ -296,10 +379,10 @@ def workload_config(cfg, args, world):
 
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
+    import copy
+
     import torch
     import torch.distributed as dist
-
-    from phantomsdr_b200.backend import B200FFT, OPT_HOST_MIRROR, OPT_STAGE_MASK
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -308,10 +391,45 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    line = run_leg(args, torch, dist, world, rank, local, dev, full=True)
+    cfg = make_cfg(args)
+    if world > 1 and not args.no_mgpu_extras and not cfg.is_real:
+        # the other exchange modes (weak scaling, same client load) and a strong-scaling leg (1024 clients in total)
+        extras = {}
+        for mode in ("spectrum", "scatter", "scatter-dma"):
+            if mode == args.mgpu_mode:
+                continue
+            a2 = copy.copy(args)
+            a2.mgpu_mode = mode
+            r = run_leg(a2, torch, dist, world, rank, local, dev, full=False)
+            if rank == 0:
+                extras[mode] = {k: r[k] for k in ("value", "ingest_msps", "ms_per_step")}
+        a3 = copy.copy(args)
+        a3.clients = max(1, args.clients // world)
+        r = run_leg(a3, torch, dist, world, rank, local, dev, full=False)
+        if rank == 0:
+            line["mgpu"] = {
+                "default_mode": args.mgpu_mode,
+                "modes_weak": {args.mgpu_mode: {k: line[k] for k in ("value", "ingest_msps", "ms_per_step")}, **extras},
+                "strong": {"clients_total": a3.clients * world, "clients_per_gpu": a3.clients, "mode": args.mgpu_mode,
+                           "ingest_msps": r["ingest_msps"], "ms_per_step": r["ms_per_step"],
+                           "note": "fixed client total: the ingest rate rises with N until rank 0's forward group bounds it"},
+            }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_leg(args, torch, dist, world, rank, local, dev, full=True):
+    from phantomsdr_b200.backend import B200FFT, OPT_PCM16, OPT_STAGE_MASK
+
     cfg = make_cfg(args)
     F, H = args.batch, args.ring
     assert H % F == 0, "--ring must be a multiple of --batch"
     n = cfg.audio_fft_size
+    wf_skip = args.waterfall_skip if args.waterfall_skip > 0 else cfg.skip_num
 
     eng = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, cfg.brightness_offset, device=local)
     eng.set_output_additional_size(n)
@@ -320,17 +438,20 @@ def run_b200(args):
     eng.set_hop_ring(HR)
     eng.set_batch_frames(F)
     eng.set_pipeline(args.banks)
+    if args.pcm16:
+        eng.set_option(OPT_PCM16, 1)
+    eng.set_waterfall_cadence(wf_skip)
     eng.clients_create(args.clients, n, cfg.audio_sps)
     scatter = world > 1 and args.mgpu_mode in ("scatter", "scatter-dma") and not cfg.is_real
     dma = args.mgpu_mode == "scatter-dma"
     if scatter:
         # the (l, r)-sorted client list of the WHOLE job, split into contiguous equal blocks
         from phantomsdr_b200.parallel import partition_clients
-        everyone = client_table(cfg, args.clients * world, 0)
+        everyone = client_table(cfg, args.clients * world, 0, args.modes)
         parts = partition_clients([(c.l, c.r) for c in everyone], world)
         my_clients = [everyone[i] for i in parts[rank]]
     else:
-        my_clients = client_table(cfg, args.clients, rank)
+        my_clients = client_table(cfg, args.clients, rank, args.modes)
     for i, c in enumerate(my_clients):
         eng.client_open(i, c.l, c.mid, c.r, c.mode)
     stream = torch.cuda.Stream(device=dev)  # a real (non-legacy) stream shared by torch/NCCL and the engine
@@ -349,6 +470,7 @@ def run_b200(args):
 
     # ---- scatter mode: IPC-mapped peer banks + flags ----
     peer_ready, my_ready, r0_consumed, my_consumed = [], None, [], None
+    ipc_opened = []
     if scatter:
         def sub_band(block):
             """<= 2 half-open ranges of spectrum indices covering every slice of the block (src/websocket.cpp:182)."""
@@ -374,8 +496,11 @@ def run_b200(args):
         if rank == 0:
             ptrs = []
             for g in range(1, world):
-                ptrs.append(eng.ipc_open(table[g]["spec"]) + eng.spectrum_offset)
-                peer_ready.append(eng.ipc_open(table[g]["flags"]))          # flag 0 of rank g: "bank k has landed"
+                sp = eng.ipc_open(table[g]["spec"])
+                fl = eng.ipc_open(table[g]["flags"])
+                ipc_opened += [sp, fl]
+                ptrs.append(sp + eng.spectrum_offset)
+                peer_ready.append(fl)                                       # flag 0 of rank g: "bank k has landed"
                 r0_consumed.append(flags + 8 * g)                           # flag g of rank 0: "rank g is done with bank k"
             eng.set_peer_spectra(ptrs)
             for g in range(1, world):
@@ -386,44 +511,43 @@ def run_b200(args):
                 eng.set_option(OPT_PEER_STORES, 0)
         else:
             my_ready = flags
-            my_consumed = eng.ipc_open(table[0]["flags"]) + 8 * rank
+            f0 = eng.ipc_open(table[0]["flags"])
+            ipc_opened.append(f0)
+            my_consumed = f0 + 8 * rank
         dist.barrier()
 
-    frame_num = 0
-    batch_no = 0
+    state = {"frame_num": 0, "batch_no": 0}
     comm = torch.cuda.Stream(device=dev) if (world > 1 and not scatter) else None
     ev_ready = [torch.cuda.Event() for _ in range(args.banks)]
     ev_done = [torch.cuda.Event() for _ in range(args.banks)]
 
-    def step():
-        nonlocal frame_num, batch_no
-        for g in range(H // F):
-            bank = batch_no % args.banks
-            eng.select_bank(bank)
-            if scatter:
-                seq = batch_no + 1
-                if rank == 0 and dma:
-                    eng.execute_device(g * F, F)
-                    if seq > args.banks:          # peers must have handed this bank back before the DMA overwrites it
-                        eng.enqueue_wait(2, r0_consumed, seq - args.banks)
-                    eng.push_peers(F)             # copy engines: every rank's sub-band of the batch, off the SMs
-                    eng.enqueue_signal(2, peer_ready, seq)
-                    eng.clients_execute_device(frame_num, F)
-                elif rank == 0:
-                    if seq > args.banks:          # peers must have handed this bank back
-                        eng.enqueue_wait(False, r0_consumed, seq - args.banks)
-                    eng.execute_device(g * F, F)  # pass 2 also stores every rank's sub-band into that rank's bank
-                    eng.enqueue_signal(False, peer_ready, seq)
-                    eng.clients_execute_device(frame_num, F)
-                else:
-                    eng.enqueue_wait(True, [my_ready], seq)
-                    eng.clients_execute_device(frame_num, F)
-                    eng.enqueue_signal(True, [my_consumed], seq)
-                frame_num += F
-                batch_no += 1
-                continue
+    def batch(hop0):
+        """Forward group of hops hop0.. on the ingest rank, the exchange step, every rank's clients - one batch of F frames."""
+        frame_num, batch_no = state["frame_num"], state["batch_no"]
+        bank = batch_no % args.banks
+        eng.select_bank(bank)
+        if scatter:
+            seq = batch_no + 1
+            if rank == 0 and dma:
+                eng.execute_device(hop0, F)
+                if seq > args.banks:          # peers must have handed this bank back before the DMA overwrites it
+                    eng.enqueue_wait(2, r0_consumed, seq - args.banks)
+                eng.push_peers(F)             # copy engines: every rank's sub-band of the batch, off the SMs
+                eng.enqueue_signal(2, peer_ready, seq)
+                eng.clients_execute_device(frame_num, F)
+            elif rank == 0:
+                if seq > args.banks:          # peers must have handed this bank back
+                    eng.enqueue_wait(False, r0_consumed, seq - args.banks)
+                eng.execute_device(hop0, F)  # pass 2 also stores every rank's sub-band into that rank's bank
+                eng.enqueue_signal(False, peer_ready, seq)
+                eng.clients_execute_device(frame_num, F)
+            else:
+                eng.enqueue_wait(True, [my_ready], seq)
+                eng.clients_execute_device(frame_num, F)
+                eng.enqueue_signal(True, [my_consumed], seq)
+        else:
             if rank == 0:
-                eng.execute_device(g * F, F)      # waits for this bank's previous clients, then FFT + pyramid
+                eng.execute_device(hop0, F)      # waits for this bank's previous clients, then FFT + pyramid
             else:
                 eng.bank_acquire()                # the broadcast may overwrite the bank once its clients are done
             if world > 1:
@@ -435,8 +559,12 @@ def run_b200(args):
                     ev_done[bank].record(comm)
                 eng.client_stream_wait_event(ev_done[bank].cuda_event)
             eng.clients_execute_device(frame_num, F)
-            frame_num += F
-            batch_no += 1
+        state["frame_num"] += F
+        state["batch_no"] += 1
+
+    def step():
+        for g in range(H // F):
+            batch(g * F)
 
     def barrier():
         if world > 1:
@@ -470,8 +598,68 @@ def run_b200(args):
         launches = int(lt.item())
     ms_step = ms_total / args.steps
     samples_per_step = H * cfg.hop_samples
-    value = world * samples_per_step / (ms_step * 1e-3) / 1e6
     ingest = samples_per_step / (ms_step * 1e-3) / 1e6
+    value = world * ingest  # VALUE_DEF
+
+    # ---- e2e at N > 1: rank 0 ingests from HOST buffers, the exchange step, every rank copies its results to the host ----
+    e2e = None
+    h = n // 2
+    pcm_bytes = 2 if args.pcm16 else 4
+    nblk = max(2, args.e2e_frames // F)
+    if full and not args.no_e2e and world > 1:
+        host_in = [torch.empty((F, cfg.hop_floats), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+        if rank == 0:
+            for t_ in host_in:
+                t_.normal_(0, 1e-3)
+        outs = [dict(pcm=eng.pinned(pcm_bytes * F * args.clients * h, np.uint8), pwr=eng.pinned(4 * F * args.clients, np.float32),
+                     valid=eng.pinned(F * args.clients, np.uint8)) for _ in range(2)]
+        pyr_host = torch.empty((F, eng.pyramid_stride), dtype=torch.int8).pin_memory() if rank == 0 else None
+        copy_s = torch.cuda.Stream(device=dev)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+
+        def e2e_multi(blocks):
+            for k in range(blocks):
+                half = k & 1
+                hop0 = half * (F + 1)  # two disjoint regions of the hop ring (HR >= 2 F + 2), one per block in flight
+                if rank == 0:
+                    # H2D of the block's F new halves into the ring slots the forward group of this batch reads
+                    with torch.cuda.stream(copy_s):
+                        if k >= 2:
+                            copy_s.wait_event(ev_free[half])  # the forward group of block k - 2 read this region
+                        for f in range(F):
+                            ring_t[hop0 + 1 + f].copy_(host_in[half][f], non_blocking=True)
+                        ev_in[half].record(copy_s)
+                    stream.wait_event(ev_in[half])
+                if k >= 2:
+                    eng.clients_fetch_wait(half)  # the host buffers of block k - 2 are about to be reused
+                batch(hop0)
+                if rank == 0:
+                    ev_free[half].record(stream)
+                    q = torch.as_tensor(eng.device_quantized(F), device=dev)
+                    pyr_host.copy_(q, non_blocking=True)  # (engine stream, behind the forward group)
+                eng.clients_fetch_async(half, F, outs[half]["pcm"], outs[half]["pwr"], outs[half]["valid"])
+            for half in range(min(2, blocks)):
+                eng.clients_fetch_wait(half)
+            eng.join_streams()
+            torch.cuda.synchronize()
+
+        e2e_multi(3)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_multi(nblk)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e_ingest = nblk * F * cfg.hop_samples / dt / 1e6
+        e2e = {"value": world * e2e_ingest, "unit": UNIT, "ingest_msps": e2e_ingest,
+               "h2d_bytes_per_step": cfg.hop_floats * 4 * H,
+               "d2h_bytes_per_step": (eng.pyramid_bytes + world * args.clients * (h * pcm_bytes + 5)) * H,
+               "frames_timed": nblk * F,
+               "path": f"rank 0: {F} new halves per batch from pinned host memory (H2D on a copy stream) -> forward group -> exchange "
+                       f"({args.mgpu_mode}) -> every rank's clients -> every rank's PCM/pwr/valid (b200_clients_fetch_async) and rank 0's "
+                       "pyramid back to pinned host memory; two batches in flight; value = ingest x client shards (VALUE_DEF)"}
 
     if scatter:
         barrier()
@@ -480,7 +668,7 @@ def run_b200(args):
         assert eng.flag_error == 0, "a flag wait timed out"
     # ---- roofline of the dominant kernel group (forward FFT + waterfall), timed alone on rank 0 ----
     roofline, breakdown = None, {}
-    if rank == 0:
+    if rank == 0 and full:
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -489,6 +677,7 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         bytes_frame = algorithmic_bytes_per_frame(cfg)
+        eng.set_waterfall_cadence(1)  # the roofline counts a pyramid per frame
 
         def time_fwd(mask, reps=20):
             eng.set_option(OPT_STAGE_MASK, mask)
@@ -509,6 +698,7 @@ def run_b200(args):
         achieved = bytes_frame / t_fwd / 1e9
         for name, mask in (("fft_pass1", 1), ("fft_pass2", 2), ("pyramid", 4)):
             breakdown[name + "_us_per_frame"] = round(time_fwd(mask) * 1e6, 3)
+        eng.set_waterfall_cadence(wf_skip)
         # client kernels alone
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -516,137 +706,122 @@ def run_b200(args):
         a.record(stream)
         reps = 20
         for r_ in range(reps):
-            eng.clients_execute_device(frame_num, F)
-            frame_num += F
+            eng.clients_execute_device(state["frame_num"], F)
+            state["frame_num"] += F
         eng.join_streams()
         b.record(stream)
         torch.cuda.synchronize()
         breakdown["clients_us_per_frame"] = round(a.elapsed_time(b) * 1e3 / (reps * F), 3)
         breakdown["forward_us_per_frame"] = round(t_fwd * 1e6, 3)
-        traffic = None
+        try:  # the library transform alone, on the same box (yardstick, not part of the product)
+            breakdown["cufft_bare_transform_us_per_frame"] = round(cufft_yardstick(torch, cfg, min(F, 32)), 3)
+        except Exception as exc:
+            breakdown["cufft_bare_transform_us_per_frame"] = f"unavailable: {exc!r}"
+        traffic, traffic_src = None, None
         try:
-            tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
-            if tr.get("batch") == F and not cfg.is_real and args.fft_log2 == 20:
+            tr = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+            if tr.get("batch") == F and tr.get("is_real") == cfg.is_real and tr.get("fft_log2") == args.fft_log2:
                 traffic = tr["dram_bytes_per_launch_group"]
+                traffic_src = tr.get("source")
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "forward FFT + waterfall (fft_pass1 + fft_pass2 + pyramid, one launch each per "
                                              f"{F} frames)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src,
                     "peak_source": which, "algorithmic_bytes_per_frame": bytes_frame,
                     "algorithmic_bytes_per_launch_group": bytes_frame * F, "us_per_frame": t_fwd * 1e6}
 
-    # ---- e2e: same frames through the reference-facing C-ABI with HOST buffers ----
+    # ---- e2e at N = 1: same frames through the reference-facing C-ABI with HOST buffers ----
     # b200_submit_block / b200_wait_block = load_*_input + execute + signal_loop for F frames per call, pipelined:
-    # H2D of block k+1, kernels of block k, D2H of block k's results (pyramid + PCM/pwr/valid) on three streams.
-    e2e = None
-    if not args.no_e2e:
+    # H2D of block k+1, kernels of block k, D2H of block k's results (pyramid + PCM/pwr/valid) on their own streams.
+    e2e_raw = None
+    if full and not args.no_e2e and world == 1:
         eng.join_streams()
         eng.sync()
-        h = n // 2
-        nblk = max(2, args.e2e_frames // F)
         rs = np.random.default_rng(0x5EED + 3 + rank)
         sets = []
         for _ in range(2):  # two blocks in flight -> two sets of pinned host buffers
-            halves = [eng.malloc(cfg.hop_floats) for _ in range(F)]
-            for hb in halves:
-                hb[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
-            sets.append(dict(halves=halves,
-                             pcm=eng.pinned(4 * F * args.clients * h, np.int32),
+            sets.append(dict(pcm=eng.pinned(pcm_bytes * F * args.clients * h, np.uint8),
                              pwr=eng.pinned(4 * F * args.clients, np.float32),
                              valid=eng.pinned(F * args.clients, np.uint8),
                              pyr=eng.pinned(F * eng.pyramid_bytes, np.int8)))
-        prime = eng.malloc(cfg.hop_floats)
-        prime[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
+        n_send = len(range(0, F, wf_skip)) if F % wf_skip == 0 else None  # send frames per block (exact when skip | F)
+        dbytes_frame = (eng.pyramid_bytes / wf_skip if n_send else eng.pyramid_bytes) + args.clients * (h * pcm_bytes + 5)
 
-        def e2e_run(blocks, f0):
+        def host_halves(dt):
+            halves_sets = []
+            for _ in range(2):
+                halves = []
+                for _k in range(F):
+                    hb = eng.pinned(cfg.hop_floats * np.dtype(dt).itemsize, dt)
+                    if dt == np.float32:
+                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
+                    elif dt == np.int16:
+                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 33.0).astype(np.int16)       # ~1e-3 full scale
+                    else:
+                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 2.0 + 128.0).astype(np.uint8)
+                    halves.append(hb)
+                halves_sets.append(halves)
+            return halves_sets
+
+        def e2e_run(halves_sets, prime, blocks, f0):
             eng.stream_prime(prime)
             for k in range(blocks):
                 st = sets[k & 1]
                 if k >= 2:
                     eng.wait_block()  # block k-2 used this buffer set
-                eng.submit_block(st["halves"], f0 + k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
+                eng.submit_block(halves_sets[k & 1], f0 + k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
             for _ in range(min(2, blocks)):
                 eng.wait_block()
 
-        e2e_run(3, 0)  # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        e2e_run(nblk, 3 * F)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        hbytes = cfg.hop_floats * 4
-        dbytes = eng.pyramid_bytes + args.clients * h * 4 + args.clients * 5
-        e2e = {"value": world * nblk * F * cfg.hop_samples / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": hbytes * H, "d2h_bytes_per_step": dbytes * H,
-               "frames_timed": nblk * F,
-               "path": f"b200_submit_block / b200_wait_block: {F} frames per call from pinned host halves "
-                       "(H2D of every new half) -> forward FFT + pyramid -> clients -> D2H of the int8 pyramid and "
-                       "PCM/pwr/valid of every frame; two blocks in flight; every rank drives its own host path"}
-
-    e2e_raw = None
-    if e2e is not None and args.e2e_raw and not cfg.is_real:
-        try:
-            from phantomsdr_b200.backend import OPT_INPUT_FORMAT, _FMT_OF_DTYPE
-            dt = np.int16 if args.e2e_raw == "s16" else np.uint8
-            eng.join_streams()
-            eng.sync()
-            eng.set_option(OPT_INPUT_FORMAT, _FMT_OF_DTYPE[np.dtype(dt).name])
-            rawsets = []
-            for _ in range(2):
-                halves = []
-                for _k in range(F):
-                    hb = eng.pinned(cfg.hop_floats * np.dtype(dt).itemsize, dt)
-                    if dt == np.int16:
-                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 33.0).astype(np.int16)       # ~1e-3 full scale
-                    else:
-                        hb[:] = (rs.standard_normal(cfg.hop_floats) * 2.0 + 128.0).astype(np.uint8)
-                    halves.append(hb)
-                rawsets.append(halves)
-            prime_raw = eng.pinned(cfg.hop_floats * np.dtype(dt).itemsize, dt)
-            prime_raw[:] = rawsets[0][0]
-
-            def raw_run(blocks, f0):
-                eng.stream_prime(prime_raw)
-                for k in range(blocks):
-                    st = sets[k & 1]
-                    if k >= 2:
-                        eng.wait_block()
-                    eng.submit_block(rawsets[k & 1], f0 + k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
-                for _ in range(min(2, blocks)):
-                    eng.wait_block()
-
-            raw_run(3, 0)
-            barrier()
+        def e2e_measure(dt):
+            hs = host_halves(dt)
+            e2e_run(hs, hs[0][0], 3, 0)  # warm-up
             t0 = time.perf_counter()
-            raw_run(nblk, 3 * F)
-            dtm = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([dtm], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dtm = float(t.item())
-            e2e_raw = {"value": world * nblk * F * cfg.hop_samples / dtm / 1e6, "unit": UNIT, "format": args.e2e_raw,
-                       "h2d_bytes_per_step": cfg.hop_floats * np.dtype(dt).itemsize * H, "d2h_bytes_per_step": dbytes * H,
-                       "frames_timed": nblk * F,
-                       "path": "as e2e, but the halves are raw ADC samples and SampleConverter (src/samplereader.cpp:29-66) runs "
-                               "inside FFT pass 1 (generic pass kernels)"}
-        except Exception as exc:
-            e2e_raw = {"value": None, "unit": UNIT, "format": args.e2e_raw, "error": repr(exc)}
+            e2e_run(hs, hs[0][0], nblk, 3 * F)
+            return time.perf_counter() - t0
+
+        dt = e2e_measure(np.float32)
+        common = f"-> forward FFT + pyramid (every {wf_skip} frame(s)) -> clients -> D2H of the int8 pyramids and " \
+                 f"{'int16' if args.pcm16 else 'int32'} PCM / pwr / valid of every frame; two blocks in flight"
+        e2e = {"value": nblk * F * cfg.hop_samples / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": cfg.hop_floats * 4 * H, "d2h_bytes_per_step": int(dbytes_frame * H),
+               "frames_timed": nblk * F,
+               "path": f"b200_submit_block / b200_wait_block: {F} frames per call from pinned host float halves (H2D of every new half) "
+                       + common}
+        if args.e2e_raw:
+            try:
+                from phantomsdr_b200.backend import OPT_INPUT_FORMAT, _FMT_OF_DTYPE
+                rdt = np.int16 if args.e2e_raw == "s16" else np.uint8
+                eng.join_streams()
+                eng.sync()
+                eng.set_option(OPT_INPUT_FORMAT, _FMT_OF_DTYPE[np.dtype(rdt).name])
+                dtm = e2e_measure(rdt)
+                e2e_raw = {"value": nblk * F * cfg.hop_samples / dtm / 1e6, "unit": UNIT, "format": args.e2e_raw,
+                           "h2d_bytes_per_step": cfg.hop_floats * np.dtype(rdt).itemsize * H, "d2h_bytes_per_step": int(dbytes_frame * H),
+                           "frames_timed": nblk * F,
+                           "path": "as e2e, but the halves are raw ADC samples: SampleConverter (src/samplereader.cpp:29-66) runs inside "
+                                   "FFT pass 1 " + common}
+            except Exception as exc:
+                e2e_raw = {"value": None, "unit": UNIT, "format": args.e2e_raw, "error": repr(exc)}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and full and not args.no_cpu_baseline:
         try:
-            fps_probe, _ = cpu_reference_run(cfg, args.clients, frames=2, warm=1)
-            frames = args.cpu_frames or int(max(4, min(2000, 15.0 * fps_probe)))
-            fps, info = cpu_reference_run(cfg, args.clients, frames=frames, warm=1)
+            fps_probe, _ = cpu_reference_run(cfg, args.clients, frames=2, warm=1, modes=args.modes)
+            frames = args.cpu_frames or int(max(4, min(2000, 12.0 * fps_probe)))
+            fps, info = cpu_reference_run(cfg, args.clients, frames=frames, warm=1, modes=args.modes)
             cpu_baseline = {"value": fps * cfg.hop_samples / 1e6, "unit": UNIT, **info}
+            # the reference's default is fft_threads = 1 (src/spectrumserver.cpp:39): the same sample with a one-thread FFT
+            fps1, info1 = cpu_reference_run(cfg, args.clients, frames=max(4, frames // 3), warm=1, modes=args.modes, fft_threads=1)
+            cpu_baseline["fft_threads_1"] = {"value": fps1 * cfg.hop_samples / 1e6, "unit": UNIT,
+                                             "split_ms_per_frame": info1["split_ms_per_frame"]}
         except Exception as exc:  # the oracle is test infrastructure; its absence must not hide the GPU number
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                             "sample": f"unavailable: {exc!r}"}
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -661,17 +836,23 @@ def run_b200(args):
             "ingest_msps": ingest,
             "realtime_margin": ingest / (cfg.sps / 1e6),
         }
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if rank == 0 or scatter:
+            for ptr in ipc_opened:
+                eng.ipc_close(ptr)
+        dist.barrier()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
     eng.close()
+    return line
 
 
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "cufft":
+        run_cufft(args)
     else:
         run_b200(args)
 

@@ -267,6 +267,13 @@ void *b200_device_valid(b200_engine *e); /* uint8 [frames][max_clients] */
 /* Copy the results of the last b200_clients_execute_device (frame index `frame` of the batch) to
  * host buffers laid out as in b200_clients_execute. Synchronous. */
 int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_out, uint8_t *valid_out);
+/* Asynchronous batch form of b200_clients_fetch: enqueue the device->host copies of the LAST client batch (nframes frames
+ * of PCM [frame][slot][n/2], pwr [frame][slot], valid [frame][slot]; page-locked destinations) behind its kernels and
+ * return; b200_clients_fetch_wait(slot) blocks until they have landed. Two slots (0 / 1), so the copies of batch k
+ * overlap the kernels of batch k + 1. This is the hand-off a pool of AudioEncoder::process threads consumes
+ * (src/signal.cpp:287-291, src/audio.cpp:65-82) without a device-wide wait. */
+int b200_clients_fetch_async(b200_engine *e, int slot, int nframes, void *pcm_out, float *pwr_out, uint8_t *valid_out);
+int b200_clients_fetch_wait(b200_engine *e, int slot);
 /* Test tap: audio_real[0..n/2) before DC removal (signal.cpp:274) of the last executed frame,
  * copied to host float [max_clients][n/2]. */
 int b200_clients_read_pre_dc(b200_engine *e, float *out);

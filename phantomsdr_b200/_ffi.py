@@ -81,6 +81,8 @@ SIGNATURES = {
     "b200_wait_block": (_i, [_vp]),
     "b200_waterfall_gather": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "b200_launch_count": (_u64, [_vp]),
+    "b200_clients_fetch_async": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "b200_clients_fetch_wait": (_i, [_vp, _i]),
     "b200_set_waterfall_cadence": (_i, [_vp, _i]),
     "b200_set_frame_number": (_i, [_vp, _u64]),
     "b200_quant_table": (_i, [_i, _vp, _vp, _vp]),

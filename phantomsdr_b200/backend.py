@@ -308,6 +308,13 @@ class B200FFT:
         check(self.L.b200_clients_fetch(self.h, frame, _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
         return out
 
+    def clients_fetch_async(self, slot: int, nframes: int, pcm=None, pwr=None, valid=None) -> None:
+        """Enqueue the D2H copies of the last client batch into page-locked host arrays; see clients_fetch_wait."""
+        check(self.L.b200_clients_fetch_async(self.h, slot, nframes, _ptr(pcm), _ptr(pwr), _ptr(valid)))
+
+    def clients_fetch_wait(self, slot: int) -> None:
+        check(self.L.b200_clients_fetch_wait(self.h, slot))
+
     def clients_read_pre_dc(self) -> np.ndarray:
         out = np.zeros((self.max_clients, self.n_audio // 2), np.float32)
         check(self.L.b200_clients_read_pre_dc(self.h, _ptr(out)))

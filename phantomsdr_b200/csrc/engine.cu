@@ -238,7 +238,7 @@ struct b200_engine {
     // With banks > 1 the tails of batch k run on their own stream, concurrently with the forward group and the demodulation
     // of batch k + 1: they are latency-bound (serial recurrences) and occupy few SMs. Audio and PCM are double-buffered.
     cudaStream_t tstream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t ev_demod[2] = {}, ev_tail[2] = {}, ev_join = nullptr;
+    cudaEvent_t ev_demod[2] = {}, ev_tail[2] = {}, ev_join = nullptr, ev_fetch[2] = {};
     bool tail_pending[2] = {};
     int tail_buf = 0;                   // buffer the NEXT client batch uses
     int last_buf = 0;                   // buffer that holds the results of the last client batch
@@ -1227,6 +1227,8 @@ void b200_engine_destroy(b200_engine *e) {
         if (p) cudaFree(p);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->h_quant) cudaFreeHost(e->h_quant);
+    for (int i = 0; i < 2; i++)
+        if (e->ev_fetch[i]) cudaEventDestroy(e->ev_fetch[i]);
     if (e->h_abort) cudaFreeHost(e->h_abort);
     if (e->d_wf_desc) cudaFree(e->d_wf_desc);
     if (e->d_wf_out) cudaFree(e->d_wf_out);
@@ -1921,6 +1923,42 @@ int b200_clients_fetch(b200_engine *e, int frame, int32_t *pcm_out, float *pwr_o
     if (valid_out) CU(cudaMemcpyAsync(valid_out, cab.valid + (size_t)frame * mc, mc, cudaMemcpyDeviceToHost, ts));
     CU(cudaStreamSynchronize(cs));
     if (ts != cs) CU(cudaStreamSynchronize(ts));
+    return stream_check(e);
+}
+
+// Asynchronous form of b200_clients_fetch for whole batches: enqueues the device->host copies of the LAST client batch
+// (nframes frames of PCM / pwr / valid) behind its kernels, on the engine's own copy path, and returns; completion is
+// b200_clients_fetch_wait(slot). Two slots, so that the copies of batch k overlap the kernels of batch k + 1.
+int b200_clients_fetch_async(b200_engine *e, int slot, int nframes, void *pcm_out, float *pwr_out, uint8_t *valid_out) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (!e->have_clients) return fail(B200_ESTATE, "clients not created");
+    if (slot < 0 || slot > 1) return fail(B200_EINVAL, "slot must be 0 or 1");
+    if (nframes < 1 || nframes > e->batch) return fail(B200_EINVAL, "nframes %d outside 1..%d", nframes, e->batch);
+    CU(cudaSetDevice(e->device));
+    if (!e->ev_fetch[0])
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&e->ev_fetch[i], cudaEventDisableTiming));
+    const size_t mc = e->ca.max_clients, h = e->ca.h;
+    const ClientArrays cab = e->client_arrays(e->last_buf);
+    cudaStream_t cs = e->client_stream();
+    if (pwr_out) CU(cudaMemcpyAsync(pwr_out, e->ca.pwr, sizeof(float) * mc * nframes, cudaMemcpyDeviceToHost, cs));
+    if (e->tail_async()) {
+        CU(cudaEventRecord(e->ev_join, cs));
+        cs = e->d2h_stream;
+        CU(cudaStreamWaitEvent(cs, e->ev_tail[e->last_buf], 0));
+        CU(cudaStreamWaitEvent(cs, e->ev_join, 0));
+    }
+    if (pcm_out)
+        CU(cudaMemcpyAsync(pcm_out, cab.pcm, (e->opt_pcm16 ? sizeof(int16_t) : sizeof(int32_t)) * mc * h * nframes, cudaMemcpyDeviceToHost, cs));
+    if (valid_out) CU(cudaMemcpyAsync(valid_out, cab.valid, mc * nframes, cudaMemcpyDeviceToHost, cs));
+    if (e->tail_async()) CU(cudaEventRecord(e->ev_tail[e->last_buf], cs));  // the buffer is free again only when the copy has read it
+    CU(cudaEventRecord(e->ev_fetch[slot], cs));
+    return 0;
+}
+int b200_clients_fetch_wait(b200_engine *e, int slot) {
+    if (!e) return fail(B200_EINVAL, "null engine");
+    if (slot < 0 || slot > 1 || !e->ev_fetch[slot]) return fail(B200_ESTATE, "no asynchronous fetch in slot %d", slot);
+    CU(cudaSetDevice(e->device));
+    CU(cudaEventSynchronize(e->ev_fetch[slot]));
     return stream_check(e);
 }
 
