@@ -412,9 +412,20 @@ int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
     if (e->log2M != 20) return 0;
     if (getenv("B200_NO_TMA")) return 0;
     CU(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
-    const uint32_t wbox = e->is_real ? 2 * kTmaT : kTmaT;
-    int rc = make_map_2d(&e->window_map, e->d_window, e->is_real ? 2 * kS : kS, kS, wbox);
-    if (rc) return rc;
+    if (!e->is_real) {
+        int rc = make_map_2d(&e->window_map, e->d_window, kS, kS, kTmaT);
+        if (rc) return rc;
+    } else if (!e->d_winT) {
+        // r2c pass 1 builds its Hann weights from (h cos, h sin)(2 pi row / 1024), h = 1/2 (the 1/N normalisation of r2c is
+        // applied with the Hermitian split)
+        std::vector<float2> wt(kS);
+        for (int r = 0; r < kS; r++) {
+            const double a = 2.0 * M_PI * (double)r / kS;
+            wt[r] = make_float2((float)(0.5 * cos(a)), (float)(0.5 * sin(a)));
+        }
+        e->d_winT = upload_f2(wt);
+        if (!e->d_winT) return fail(B200_ENOMEM, "window table allocation failed");
+    }
     CU(cudaFuncSetAttribute(fft_pass1_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass1C));
     CU(cudaFuncSetAttribute(fft_pass1_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass1R));
     CU(cudaFuncSetAttribute(fft_pass2_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TmaSmem::kPass2));
@@ -644,6 +655,9 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
     p.twA2 = e->d_twA2;
     p.TL = e->d_TL;
     p.TH = e->d_TH;
+    p.TLr = e->d_TLr;
+    p.THr = e->d_THr;
+    p.winT = e->d_winT;
     float2 *spec = e->spec_ptr() + (size_t)f0 * e->spec_stride;
     if (!e->is_real) {
         p.shift = e->na > 1 ? 0 : 1;  // the display-aligned row order only exists in the plain two-pass transform
@@ -953,7 +967,7 @@ int alloc_batch(b200_engine *e, int frames) {
     // elements makes every run start on a 64-byte boundary, so pass 2 writes whole sectors
     CU(cudaMalloc(&e->d_spec_raw, sizeof(float2) * (e->spec_stride * frames * e->banks + 16)));
     CU(cudaMemset(e->d_spec_raw, 0, sizeof(float2) * (e->spec_stride * frames * e->banks + 16)));
-    e->d_spec = e->d_spec_raw + 15;
+    e->d_spec = e->d_spec_raw + (e->is_real ? 16 : 15);
     e->spec_map_ok = false;
     if (e->tma_ok && !e->is_real && e->spec_stride % 16 == 0) {
         // quantiser items of the stream kernel read the spectrum as rows of 16 bins starting at bin 1 (a 128-byte line)
@@ -1587,7 +1601,7 @@ int b200_set_peer_ranges(b200_engine *e, int peer, uint32_t lo0, uint32_t hi0, u
     return 0;
 }
 void *b200_device_spectrum_base(b200_engine *e) { return e ? e->d_spec_raw : nullptr; }
-size_t b200_device_spectrum_offset(b200_engine *e) { return e ? 15 * sizeof(float2) : 0; }
+size_t b200_device_spectrum_offset(b200_engine *e) { return e ? (e->is_real ? 16 : 15) * sizeof(float2) : 0; }
 void *b200_flag_buffer(b200_engine *e) {
     if (!e) return nullptr;
     if (!e->d_flags) {

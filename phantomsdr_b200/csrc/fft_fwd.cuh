@@ -60,6 +60,9 @@ struct FwdParams {
     // and pass 2 interleaves their bins, k = ka + na * k_sub
     const float2 *pre;       // [frames][na][Mb]
     int na;                  // 1 = plain two-pass transform
+    // r2c on the TMA path: Hann weights built on the fly from (h cos, h sin)(2 pi row / 1024), h = 1/2, and W_size^(2 n2 + b)
+    const float2 *winT;
+    const float2 *TLr, *THr; // W_size^j, j < 1024; W_size^(1024 j)
 };
 
 template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
@@ -620,34 +623,75 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
         }
     } else if constexpr (MODE == PYR_R2C) {
         // r2c split: X[k] = (Z[k] + conj(Z[M-k]))/2 - (i/2) W_size^k (Z[k] - conj(Z[M-k])), M = R
+        // The thread's 16 bins k = d0 .. d0+15 need Z[d0 .. d0+15] (one aligned 128-byte run) and the mirrored run
+        // Z[R-d0-15 .. R-d0] (contiguous as well, but it starts on an odd element: 64-bit loads at both ends, 128-bit
+        // in between). Twiddles: W^(d0+i) = W^d0 * W^i - one table lookup per thread, sixteen small constants per block.
         float2 *spec = p.spec + (size_t)frame * p.spec_stride;
         const float2 *Z = p.Z + (size_t)frame * R;
+        float2 a[PER], b[PER];
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(Z + d0);
+#pragma unroll
+            for (int i = 0; i < PER / 2; i++) {
+                const float4 x = src[i];
+                a[2 * i] = make_float2(x.x, x.y);
+                a[2 * i + 1] = make_float2(x.z, x.w);
+            }
+        }
+        if (d0 == 0) {  // the run that pairs with bins 0 .. 15 wraps: Z[0], Z[R-1], ..., Z[R-15]
+            b[0] = Z[0];
+#pragma unroll
+            for (int i = 1; i < PER; i++) b[i] = Z[R - i];
+        } else {
+            const float2 *m = Z + (R - d0 - (PER - 1));  // ascending addresses m[0 .. PER-1] = Z[R-d0-15 .. R-d0], b[i] = m[PER-1-i]
+            b[PER - 1] = m[0];
+            const float4 *mid = reinterpret_cast<const float4 *>(m + 1);
+#pragma unroll
+            for (int i = 0; i < (PER - 2) / 2; i++) {
+                const float4 x = mid[i];
+                b[PER - 2 - 2 * i] = make_float2(x.x, x.y);
+                b[PER - 3 - 2 * i] = make_float2(x.z, x.w);
+            }
+            b[0] = m[PER - 1];
+        }
+        const float2 w0 = cmul(__ldg(p.TLr + (d0 & 1023)), __ldg(p.THr + (d0 >> 10)));
+        float2 xs[PER];
 #pragma unroll
         for (int i = 0; i < PER; i++) {
-            const unsigned k = d0 + i;
-            const float2 a = Z[k];
-            const float2 b = Z[(R - k) & (R - 1)];
-            const float2 e = make_float2(a.x + b.x, a.y - b.y);
-            const float2 o = make_float2(a.x - b.x, a.y + b.y);
-            const float2 w = cmul(__ldg(p.TLr + (k & 1023)), __ldg(p.THr + (k >> 10)));
+            const float2 e = make_float2(a[i].x + b[i].x, a[i].y - b[i].y);
+            const float2 o = make_float2(a[i].x - b[i].x, a[i].y + b[i].y);
+            const float2 w = (i == 0) ? w0 : cmul(w0, __ldg(p.TLr + i));
             const float2 t = cmul(o, w);
             float2 x = make_float2(0.5f * (e.x + t.y), 0.5f * (e.y - t.x));
-            if (k == 0) {
-                // Nyquist bin is left unnormalised by the reference (only outbuf_len = size/2 bins are
-                // divided, src/fft_impl.cpp:152-154)
-                const float2 ny = make_float2(a.x - a.y, 0.f);
-                spec[R] = ny;
-                for (int pe = 0; pe < p.npeers; pe++)
-                    if ((R >= p.peer_lo[pe][0] && R < p.peer_hi[pe][0]) || (R >= p.peer_lo[pe][1] && R < p.peer_hi[pe][1]))
-                        (p.peers[pe] + (size_t)frame * p.spec_stride)[R] = ny;
-            }
             x.x *= p.scale;
             x.y *= p.scale;
-            spec[k] = x;
-            for (int pe = 0; pe < p.npeers; pe++)
-                if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1]))
-                    (p.peers[pe] + (size_t)frame * p.spec_stride)[k] = x;
+            xs[i] = x;
             pw[i] = __fadd_rn(__fmul_rn(x.x, x.x), __fmul_rn(x.y, x.y));
+        }
+        if (d0 == 0) {
+            // Nyquist bin is left unnormalised by the reference (only outbuf_len = size/2 bins are divided,
+            // src/fft_impl.cpp:152-154)
+            const float2 ny = make_float2(a[0].x - a[0].y, 0.f);
+            spec[R] = ny;
+            for (int pe = 0; pe < p.npeers; pe++)
+                if ((R >= p.peer_lo[pe][0] && R < p.peer_hi[pe][0]) || (R >= p.peer_lo[pe][1] && R < p.peer_hi[pe][1]))
+                    (p.peers[pe] + (size_t)frame * p.spec_stride)[R] = ny;
+        }
+        if ((reinterpret_cast<uintptr_t>(spec + d0) & 15) == 0) {
+            float4 *dst = reinterpret_cast<float4 *>(spec + d0);
+#pragma unroll
+            for (int i = 0; i < PER / 2; i++) dst[i] = make_float4(xs[2 * i].x, xs[2 * i].y, xs[2 * i + 1].x, xs[2 * i + 1].y);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PER; i++) spec[d0 + i] = xs[i];
+        }
+        for (int pe = 0; pe < p.npeers; pe++) {
+            float2 *ps = p.peers[pe] + (size_t)frame * p.spec_stride;
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const unsigned k = d0 + i;
+                if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1])) ps[k] = xs[i];
+            }
         }
     } else if constexpr (MODE == PYR_POWER) {
         // |X|^2 left by FFT pass 2 in [u2][u1] order: display bin d = u1 + N1 * ((u2 + N2/2) mod N2)

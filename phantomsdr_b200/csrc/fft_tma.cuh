@@ -104,7 +104,8 @@ struct TmaSmem {
     static constexpr size_t kPower = sizeof(float) * kS * kPP;          // 36 KiB |X|^2 tile of the fused waterfall epilogue
     static constexpr size_t kBars = 64;
     static constexpr size_t kPass1C = kStage + kTwA + kWindowC + kBars;
-    static constexpr size_t kPass1R = kStage + kTwA + kWindowR + kBars;
+    static constexpr size_t kWinTab = sizeof(float2) * kS;             // r2c: table the Hann weights are built from on the fly
+    static constexpr size_t kPass1R = kStage + kTwA + kWinTab + kBars;
     static constexpr size_t kPass2 = kStage + kTwA + kPower + kBars;
 };
 static_assert(TmaSmem::kStage >= sizeof(float2) * kS * kTmaT, "stage must hold a tile");
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
     float2 *twA = reinterpret_cast<float2 *>(smem_raw + TmaSmem::kStage);
     float *win = reinterpret_cast<float *>(smem_raw + TmaSmem::kStage + TmaSmem::kTwA);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + TmaSmem::kStage + TmaSmem::kTwA +
-                                                  (REAL ? TmaSmem::kWindowR : TmaSmem::kWindowC));
+                                                  (REAL ? TmaSmem::kWinTab : TmaSmem::kWindowC));
     uint64_t *full = bars, *wbar = bars + 1;
 
     // Work items (column tile, frame) of this CTA, item j = 0 .. nitems-1:
@@ -171,10 +172,13 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
         fence_barrier_init();
         fence_proxy_async();
     }
-    for (int i = tid; i < 32 * 32; i += kTmaThreads) twA[i] = p.twA1[i];
+    for (int i = tid; i < 32 * 32; i += kTmaThreads) {
+        twA[i] = p.twA1[i];
+        if constexpr (REAL) reinterpret_cast<float2 *>(win)[i] = p.winT[i];  // (h cos, h sin)(2 pi row / 1024), h = 1/2
+    }
     __syncthreads();
 
-    // thread 0 drives TMA: the window slice of a column tile when it changes, and one item ahead of the consumers
+    // thread 0 drives TMA: the window slice of a column tile when it changes (c2c), and one item ahead of the consumers
     auto issue_item = [&](int tile, int f) {
         mbar_expect_tx(full, sizeof(float2) * N1 * T);
         const int hopA = (p.hop0 + f) % p.nhops, hopB = (p.hop0 + f + 1) % p.nhops;
@@ -185,11 +189,12 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
         tma_load_2d(smem_raw + 3 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2) + 256, full);
     };
     auto issue_window = [&](int tile) {
-        constexpr uint32_t kWinBytes = sizeof(float) * N1 * T * (REAL ? 2 : 1);
-        mbar_expect_tx(wbar, kWinBytes);
-        for (int b = 0; b < 4; b++)
-            tma_load_2d(reinterpret_cast<unsigned char *>(win) + b * (kWinBytes / 4), &window_map, tile * T * (REAL ? 2 : 1),
-                        b * 256, wbar);
+        if constexpr (!REAL) {
+            constexpr uint32_t kWinBytes = sizeof(float) * N1 * T;
+            mbar_expect_tx(wbar, kWinBytes);
+            for (int b = 0; b < 4; b++)
+                tma_load_2d(reinterpret_cast<unsigned char *>(win) + b * (kWinBytes / 4), &window_map, tile * T, b * 256, wbar);
+        }
     };
     if (tid == 0) {
         int tile0, f0;
@@ -207,6 +212,9 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
     //   G[a] = W_M^(n2*(q + 128 a)),  B[b-1] = W_M^(32*n2*b)   ->   tw(s) = G[a] * B[b-1]  (b = 0: G[a])
     // (the IQ k1 = 0 row, q = 0 and s = 0, carries the one-slot rotation W_M^(N1*n2) instead)
     float2 G[8], B[3], rot0;
+    // r2c: a complex element holds the real samples 2 idx and 2 idx + 1, whose Hann weights 1/2 - 1/2 cos(A_row + B_b) are
+    // built on the fly: A_row from the shared table, (cos, sin) B_b = W_size^(2 n2 + b) per thread (angle addition)
+    float cB0 = 0.f, sB0 = 0.f, cB1 = 0.f, sB1 = 0.f;
     auto tw_lookup = [&](unsigned e) { return cmul(__ldg(p.TL + (e & 1023u)), __ldg(p.TH + ((e >> 10) & 1023u))); };
     int cur_tile = -1, wphase = 0;
     for (int it_local = 0; it_local < nitems; it_local++) {
@@ -220,8 +228,18 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
 #pragma unroll
             for (int b = 1; b < 4; b++) B[b - 1] = tw_lookup((unsigned)n2 * 32u * (unsigned)b);
             rot0 = tw_lookup((unsigned)N1 * (unsigned)n2);
-            mbar_wait(wbar, wphase & 1);
-            wphase++;
+            if constexpr (REAL) {
+                const unsigned e0 = 2u * (unsigned)n2, e1 = e0 + 1u;
+                const float2 w0 = cmul(__ldg(p.TLr + (e0 & 1023u)), __ldg(p.THr + (e0 >> 10)));
+                const float2 w1 = cmul(__ldg(p.TLr + (e1 & 1023u)), __ldg(p.THr + (e1 >> 10)));
+                cB0 = w0.x;
+                sB0 = -w0.y;
+                cB1 = w1.x;
+                sB1 = -w1.y;
+            } else {
+                mbar_wait(wbar, wphase & 1);
+                wphase++;
+            }
         }
         mbar_wait(full, it_local & 1);
         float2 v[RA];
@@ -229,9 +247,9 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
         for (int j = 0; j < RA; j++) {
             float2 x = sm[(r + RB * j) * T + c];
             if constexpr (REAL) {
-                const float2 w = reinterpret_cast<const float2 *>(win)[(r + RB * j) * T + c];
-                x.x *= w.x;
-                x.y *= w.y;
+                const float2 tab = reinterpret_cast<const float2 *>(win)[r + RB * j];
+                x.x *= fmaf(tab.y, sB0, fmaf(-tab.x, cB0, 0.5f));
+                x.y *= fmaf(tab.y, sB1, fmaf(-tab.x, cB1, 0.5f));
             } else {
                 const float w = win[(r + RB * j) * T + c];
                 x.x *= w;
