@@ -140,6 +140,9 @@ int b200_set_frame_number(b200_engine *e, uint64_t frame_num);
 #define B200_OPT_PYRAMID_LAG 13  /* B200_OPT_TMA 3: frames between a pass-2 tile and the pyramid blocks that ride on it (default 2) */
 #define B200_OPT_PCM16 18        /* N2: 1 = PCM rows are int16 [frame][slot][n/2] (half the D2H bytes; values identical), 0 (default) = int32
                                    as AudioEncoder::process takes them (src/audio.h:26-27). Pipelined tail kernel only. */
+#define B200_OPT_DEMOD_CHUNK 19  /* frames per warp task of the frame-chunked demodulation kernel (default 8; 0 = the sequential
+                                   one-CTA-per-client kernel only). Results are bit-identical either way. */
+#define B200_OPT_CLIENT_STAGE_MASK 20 /* profiling aid: bit0 = demodulation kernels, bit1 = tail kernel; default 3 */
 #define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */
 #define B200_OPT_STREAM_LAG1 15  /* ... frame slots between pass 1 and pass 2 of a frame in the item order (default 2) */
 #define B200_OPT_STREAM_LAG2 16  /* ... between pass 1 and the quantiser (default 4) */

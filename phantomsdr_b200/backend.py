@@ -25,6 +25,8 @@ OPT_PACKED_MATH, OPT_FWD_LANES, OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER = 9, 10, 11,
 OPT_PYRAMID_LAG = 13
 OPT_STREAM_GRID, OPT_STREAM_LAG1, OPT_STREAM_LAG2, OPT_STREAM_RING = 14, 15, 16, 17
 OPT_PCM16 = 18
+OPT_DEMOD_CHUNK = 19
+OPT_CLIENT_STAGE_MASK = 20
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 

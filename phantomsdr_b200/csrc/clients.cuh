@@ -74,6 +74,17 @@ struct ClientLaunch {
     int fchunk;          // demod kernel: frames whose inverse FFTs are batched in shared memory at once
     int cpb;             // tail kernel: clients per block
     long long *prof;     // optional: per-phase SM clock totals of block 0 (profiling aid), 8 entries
+    // frame-chunked demodulation (client_demod_warp_kernel): state is read from the `sin` copies and written to the arrays
+    // of ClientArrays; clients whose batch must be replayed sequentially (a NaN-dropped frame) are flagged in `redo`
+    const float *sin_real_prev;
+    const float *sin_real_hi;
+    const float2 *sin_bb_hi;
+    const float2 *sin_bb_last;
+    const int *sin_hi_diverged;
+    unsigned char *redo;  // [max_clients]
+    int chunk;            // frames per warp task
+    int nchunks;
+    int redo_only;        // client_demod_kernel: only the flagged clients, starting from the `sin` state
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -194,6 +205,21 @@ __global__ void __launch_bounds__(TPB) client_demod_kernel(const ClientArrays ca
     float *real_hi = ca.real_hi + (size_t)slot * h;
     float2 *bb_hi = ca.bb_hi + (size_t)slot * h;
 
+    if (cl.redo_only) {
+        // sequential replay of a client whose batch the frame-chunked kernel could not finish (a frame dropped by the NaN
+        // guard changes what later frames overlap with): start again from the state the batch began with
+        if (!cl.redo[slot]) return;
+        for (int i = tid; i < h; i += TPB) {
+            real_prev[i] = cl.sin_real_prev[(size_t)slot * h + i];
+            real_hi[i] = cl.sin_real_hi[(size_t)slot * h + i];
+            bb_hi[i] = cl.sin_bb_hi[(size_t)slot * h + i];
+        }
+        if (tid == 0) {
+            ca.bb_last[slot] = cl.sin_bb_last[slot];
+            ca.hi_diverged[slot] = cl.sin_hi_diverged[slot];
+        }
+        __syncthreads();
+    }
     if (cs.flags & CF_RESET_ALL) {  // freshly opened slot: zeroed scratch as AudioClient's ctor (signal.cpp:38-52)
         for (int i = tid; i < h; i += TPB) {
             real_prev[i] = 0.f;
@@ -327,6 +353,204 @@ __global__ void __launch_bounds__(TPB) client_demod_kernel(const ClientArrays ca
                 ca.pwr[(size_t)f * ca.max_clients + slot] = s_pw[fr];
             }
             __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frame-chunked demodulation: one WARP per (client, chunk of `cl.chunk` consecutive frames), nothing but warp-level
+// synchronisation. The inverse FFTs of different frames are independent and the overlap-add only couples a frame to its
+// predecessor, so a task that does not start at the first frame of the batch simply recomputes the predecessor's inverse
+// FFT (and, for FM, the one before that: the discriminator's first phase step needs the last overlapped sample) with the
+// very same stage code - its results are bit-identical to the sequential kernel's. Every stage of a 360-point transform is
+// 72 .. 180 butterflies: a 32-lane warp is a far better fit than a 256-thread CTA, and eight independent warps per CTA
+// overlap one another's shared-memory latency with no barrier in between.
+// A frame dropped by the NaN guard (src/signal.cpp:266-275: the overlap state does not advance) breaks the independence;
+// such clients are flagged and replayed by client_demod_kernel (redo_only) from the state the batch began with.
+// Dynamic smem: kDemodWarps * (2 n + h) float2.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDemodWarps = 8;
+
+__global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(const ClientArrays ca, const ClientLaunch cl) {
+    extern __shared__ float2 smem_c[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int task = blockIdx.x * (blockDim.x >> 5) + warp;  // (fewer than kDemodWarps warps per CTA for very long audio FFTs)
+    if (task >= cl.nactive * cl.nchunks) return;
+    const int ci = task / cl.nchunks, k = task - ci * cl.nchunks;
+    const int slot = cl.order[ci];
+    const int n = ca.n, h = ca.h;
+    float2 *bufX = smem_c + (size_t)warp * (2 * n + h);
+    float2 *bufY = bufX + n;
+    float2 *prevC = bufY + n;  // overlap state: upper half of the previous frame (SSB: .x only)
+    const ClientSlot cs = ca.slots[slot];
+    const size_t R = cl.is_real ? cl.fft_size / 2 : cl.fft_size;
+    const size_t base_idx = cl.is_real ? 0 : cl.fft_size / 2 + 1;
+    const size_t off = ((size_t)cs.l + base_idx) % R;  // src/websocket.cpp:182
+    const int len = cs.r - cs.l;
+    const int audio_m = cs.m_floor - cs.l;
+    const int mode = cs.mode;
+    const bool ssb = mode == MODE_USB || mode == MODE_LSB;
+    const bool fresh = (cs.flags & CF_RESET_ALL) != 0;
+    const int f_begin = k * cl.chunk, f_end = min(cl.nframes, f_begin + cl.chunk);
+    if (k == 0 && !fresh && cl.sin_hi_diverged[slot]) {  // state left behind by a dropped SSB frame: sequential replay
+        if (lane == 0) cl.redo[slot] = 1;
+    }
+
+    // placement of the slice of frame f into the IFFT input (signal.cpp:125-198)
+    auto gather = [&](int f) {
+        const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
+        for (int kk = lane; kk < n; kk += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            if (ssb) {
+                // c2r reads bins 0..n/2 of its input; the other half is the Hermitian mirror
+                const int k2 = (kk <= n / 2) ? kk : n - kk;
+                const int i = (mode == MODE_USB) ? (audio_m + k2) : (audio_m - k2);
+                if (i >= 0 && i < len) {
+                    v = buf[i];
+                    if (k2 == 0 || k2 == n / 2) v.y = 0.f;  // c2r ignores Im of DC / Nyquist
+                    else if (kk > n / 2) v.y = -v.y;
+                }
+            } else {
+                const int d = (kk < n / 2) ? kk : kk - n;  // positive bins [0, n/2), negative [-n/2+1, -1]; kk = n/2 stays 0
+                const int i = audio_m + d;
+                if (kk != n / 2 && i >= 0 && i < len) v = buf[i];
+            }
+            bufX[kk] = v;
+        }
+        __syncwarp();
+    };
+    // unnormalised inverse FFT of bufX (signal.cpp:138,154,214); returns the buffer that holds the result
+    auto ifft = [&]() -> float2 * {
+        float2 *xb = bufX, *yb = bufY;
+        int s = 1;
+        for (int st = 0; st < ca.nstages; st++) {
+            const int Rr = ca.radix[st];
+            if (Rr == 4) ifft_stage_fixed<4>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], 1, ca.Wn, lane, 32);
+            else if (Rr == 2) ifft_stage_fixed<2>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], 1, ca.Wn, lane, 32);
+            else if (Rr == 3) ifft_stage_fixed<3>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], 1, ca.Wn, lane, 32);
+            else if (Rr == 5) ifft_stage_fixed<5>(xb, yb, n, s, ca.mul_s[st], ca.mul_items[st], 1, ca.Wn, lane, 32);
+            else ifft_stage_generic(xb, yb, n, s, Rr, ca.mul_s[st], ca.mul_n, 1, ca.Wn, lane, 32);
+            s *= Rr;
+            float2 *t = xb;
+            xb = yb;
+            yb = t;
+            __syncwarp();
+        }
+        return xb;
+    };
+    auto sign_of = [&](int f) -> float {  // signal.cpp:160-172,223-237: parity flip of every other frame
+        const unsigned long long frame_num = cl.frame_num0 + f;
+        const int m_idx = cs.m_floor;
+        const bool negate = (frame_num & 1ull) && (((m_idx % 2 == 0) && !cl.is_real) || ((m_idx % 2 == 1) && cl.is_real));
+        return negate ? -1.f : 1.f;
+    };
+    // the upper half of a transformed frame, as the next frame will overlap it
+    auto take_upper = [&](const float2 *x, float sg) {
+        for (int t = lane; t < h; t += 32) {
+            if (ssb) prevC[t] = make_float2(sg * ((mode == MODE_USB) ? x[h + t].x : x[n - 1 - (h + t)].x), 0.f);
+            else prevC[t] = make_float2(sg * x[h + t].x, sg * x[h + t].y);
+        }
+        __syncwarp();
+    };
+
+    // ---- the state this task starts from ----
+    float2 last = make_float2(0.f, 0.f);  // FM: the last overlapped sample of the previous frame
+    if (k == 0) {
+        for (int t = lane; t < h; t += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            if (!fresh) v = ssb ? make_float2(cl.sin_real_prev[(size_t)slot * h + t], 0.f) : cl.sin_bb_hi[(size_t)slot * h + t];
+            prevC[t] = v;
+        }
+        if (!fresh) last = cl.sin_bb_last[slot];
+        __syncwarp();
+    } else {
+        float2 hi2 = make_float2(0.f, 0.f);  // upper-half sample h - 1 of frame f_begin - 2, as frame f_begin - 1 overlapped it
+        if (mode == MODE_FM) {
+            if (f_begin >= 2) {
+                gather(f_begin - 2);
+                const float2 *x = ifft();
+                const float sg = sign_of(f_begin - 2);
+                hi2 = make_float2(sg * x[n - 1].x, sg * x[n - 1].y);
+                __syncwarp();
+            } else if (!fresh) {
+                hi2 = cl.sin_bb_hi[(size_t)slot * h + h - 1];
+            }
+        }
+        gather(f_begin - 1);
+        const float2 *x = ifft();
+        const float sg = sign_of(f_begin - 1);
+        if (!ssb) last = make_float2(__fadd_rn(sg * x[h - 1].x, hi2.x), __fadd_rn(sg * x[h - 1].y, hi2.y));
+        take_upper(x, sg);
+    }
+
+    // ---- the task's own frames, in order ----
+    for (int f = f_begin; f < f_end; f++) {
+        const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
+        float pw = 0.f;  // slice power (signal.cpp:117-119)
+        for (int i = lane; i < len; i += 32) {
+            const float2 v = buf[i];
+            pw += v.x * v.x + v.y * v.y;
+        }
+        pw = warp_sum(pw);
+        gather(f);
+        float2 *x = ifft();
+        float2 *y = (x == bufX) ? bufY : bufX;  // free scratch
+        const float sg = sign_of(f);
+        float *audio = ca.audio_pre + ((size_t)f * ca.max_clients + slot) * h;
+        int nan_seen = 0;
+        if (ssb) {
+            // signal.cpp:155-172: (LSB: time reverse), parity negate, overlap-add
+            for (int t = lane; t < h; t += 32) {
+                const float lo = (mode == MODE_USB) ? x[t].x : x[n - 1 - t].x;
+                const float o = __fadd_rn(sg * lo, prevC[t].x);
+                nan_seen |= (o != o);
+                audio[t] = o;
+            }
+        } else {
+            // signal.cpp:200-263
+            for (int t = lane; t < h; t += 32) {
+                const float2 lo = x[t], old = prevC[t];
+                y[t] = make_float2(__fadd_rn(sg * lo.x, old.x), __fadd_rn(sg * lo.y, old.y));
+            }
+            __syncwarp();
+            for (int t = lane; t < h; t += 32) {
+                const float2 b = y[t];
+                float o;
+                if (mode == MODE_AM) {
+                    o = __fsqrt_rn(__fadd_rn(__fmul_rn(b.x, b.x), __fmul_rn(b.y, b.y)));  // dsp.cpp:116-126
+                } else {
+                    const float2 pv = (t == 0) ? last : y[t - 1];
+                    const float c = pv.x, d = -pv.y;  // buf[i] * conj(prev), dsp.cpp:27-35
+                    const float re = __fsub_rn(__fmul_rn(b.x, c), __fmul_rn(b.y, d));
+                    const float im = __fadd_rn(__fmul_rn(b.x, d), __fmul_rn(b.y, c));
+                    o = atan2f(im, re);
+                }
+                nan_seen |= (o != o);
+                audio[t] = o;
+            }
+            last = y[h - 1];
+            __syncwarp();
+        }
+        nan_seen = __any_sync(0xffffffffu, nan_seen);
+        take_upper(x, sg);
+        if (lane == 0) {
+            ca.valid_a[(size_t)f * ca.max_clients + slot] = nan_seen ? 0 : 1;
+            ca.pwr[(size_t)f * ca.max_clients + slot] = pw;
+            if (nan_seen) cl.redo[slot] = 1;
+        }
+    }
+
+    // ---- the last task of a client leaves the state for the next batch ----
+    if (k == cl.nchunks - 1) {
+        for (int t = lane; t < h; t += 32) {
+            const size_t o = (size_t)slot * h + t;
+            ca.real_prev[o] = ssb ? prevC[t].x : (fresh ? 0.f : cl.sin_real_prev[o]);
+            ca.real_hi[o] = fresh ? 0.f : cl.sin_real_hi[o];
+            ca.bb_hi[o] = ssb ? (fresh ? make_float2(0.f, 0.f) : cl.sin_bb_hi[o]) : prevC[t];
+        }
+        if (lane == 0) {
+            ca.bb_last[slot] = ssb ? (fresh ? make_float2(0.f, 0.f) : cl.sin_bb_last[slot]) : last;
+            ca.hi_diverged[slot] = 0;
         }
     }
 }

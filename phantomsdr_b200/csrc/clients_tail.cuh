@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
 
     // bounded waits: a stage that never gets its chunk is a bug in this file - flag it and leave instead of hanging
     auto wait_bar = [&](uint64_t *bar, unsigned parity) -> bool {
+        const int bar_id = (int)(bar - bars);  // (edge, full/empty, slot) - reported when the wait expires
         if (mbar_try_wait(bar, parity)) return true;
         unsigned long long t0 = 0;
         for (unsigned spins = 1;; spins++) {
@@ -132,8 +133,7 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
                 const unsigned long long now = global_ns();
                 if (t0 == 0) t0 = now;
                 else if (now - t0 > 2000000000ull) {
-                    s_abort = 1;
-                    *st.err = 1;
+                    if (atomicCAS(&s_abort, 0, 1) == 0) atomicCAS(st.err, 0, 10000 + warp * 100 + bar_id);  // first stage to give up
                     return false;
                 }
             }

@@ -247,6 +247,11 @@ struct b200_engine {
     int *h_tail_err = nullptr;          // pinned mirror of t2.err
     int last_client_frames = 0;
     int demod_fchunk = 1;
+    int opt_client_mask = 3;            // profiling aid: bit0 = demodulation kernels, bit1 = tail kernel
+    int opt_demod_chunk = 8;            // frames per warp task of the frame-chunked demodulation (0 = sequential kernel only)
+    int demod_wpc = 0;                  // warps per CTA of client_demod_warp_kernel (0 = audio FFT too long: sequential kernel)
+    int cstate = 0;                     // which copy of the overlap state the next client batch reads
+    unsigned char *d_redo = nullptr;
     long long *d_prof = nullptr;
 
     // pipelined host-block streaming (b200_stream_prime / b200_submit_block / b200_wait_block)
@@ -292,6 +297,15 @@ struct b200_engine {
         c.pcm += (size_t)b * F * mc * h;
         c.valid += (size_t)b * F * mc;
         return c;
+    }
+    // the two copies of the overlap state (frame-chunked demodulation reads one and writes the other)
+    void state_ptrs(int which, float *&real_prev, float *&real_hi, float2 *&bb_hi, float2 *&bb_last, int *&hi_div) const {
+        const size_t mc = ca.max_clients, h = ca.h;
+        real_prev = ca.real_prev + (size_t)which * mc * h;
+        real_hi = ca.real_hi + (size_t)which * mc * h;
+        bb_hi = ca.bb_hi + (size_t)which * mc * h;
+        bb_last = ca.bb_last + (size_t)which * mc;
+        hi_div = ca.hi_diverged + (size_t)which * mc;
     }
 };
 
@@ -630,7 +644,8 @@ int stream_check(b200_engine *e) {
     if (e->stream_used && e->h_abort && *e->h_abort)
         return fail(B200_ECUDA, "forward stream kernel: a bounded wait expired (protocol timeout); results of the batch are incomplete");
     if (e->h_tail_err && *e->h_tail_err)
-        return fail(B200_ECUDA, "client tail pipeline: a bounded wait expired (protocol timeout); results of the batch are incomplete");
+        return fail(B200_ECUDA, "client tail pipeline: a bounded wait expired (protocol timeout, code %d = 10000 + 100 * stage + barrier); "
+                                "results of the batch are incomplete", *e->h_tail_err);
     return 0;
 }
 
@@ -1029,13 +1044,51 @@ std::vector<int> factorize(int n) {
 
 constexpr int kDemodThreads = 256;
 
-int launch_demod(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
+int launch_demod(b200_engine *e, const ClientArrays &ca_in, const ClientLaunch &cl_in) {
     const size_t smem = sizeof(float2) * 2 * e->ca.n * e->demod_fchunk;
-    if (cl.nactive == 0) {  // preparation call from clients_create
+    const size_t per_warp = sizeof(float2) * (2 * (size_t)e->ca.n + e->ca.h);
+    if (cl_in.nactive == 0) {  // preparation call from clients_create
         CU(cudaFuncSetAttribute(client_demod_kernel<kDemodThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        e->demod_wpc = (int)std::min<size_t>(kDemodWarps, (200 * 1024) / per_warp);
+        if (e->demod_wpc >= 1)
+            CU(cudaFuncSetAttribute(client_demod_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * e->demod_wpc)));
         return 0;
     }
-    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, e->client_stream()>>>(ca, cl);
+    cudaStream_t cs = e->client_stream();
+    ClientArrays ca = ca_in;
+    ClientLaunch cl = cl_in;
+    if (e->opt_demod_chunk > 0 && e->demod_wpc >= 1) {
+        // frame-chunked: read state copy `cstate`, write the other one; then replay the (rare) flagged clients sequentially
+        float *rp, *rh;
+        float2 *bh, *bl;
+        int *hd;
+        e->state_ptrs(e->cstate, rp, rh, bh, bl, hd);
+        cl.sin_real_prev = rp;
+        cl.sin_real_hi = rh;
+        cl.sin_bb_hi = bh;
+        cl.sin_bb_last = bl;
+        cl.sin_hi_diverged = hd;
+        e->state_ptrs(e->cstate ^ 1, ca.real_prev, ca.real_hi, ca.bb_hi, ca.bb_last, ca.hi_diverged);
+        cl.redo = e->d_redo;
+        cl.chunk = std::max(1, std::min(e->opt_demod_chunk, cl.nframes));
+        cl.nchunks = (cl.nframes + cl.chunk - 1) / cl.chunk;
+        cl.redo_only = 0;
+        CU(cudaMemsetAsync(e->d_redo, 0, (size_t)e->ca.max_clients, cs));
+        const int tasks = cl.nactive * cl.nchunks;
+        client_demod_warp_kernel<<<(tasks + e->demod_wpc - 1) / e->demod_wpc, 32 * e->demod_wpc, per_warp * e->demod_wpc, cs>>>(ca, cl);
+        e->launches++;
+        CU(cudaGetLastError());
+        cl.redo_only = 1;
+        client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, cs>>>(ca, cl);
+        e->launches++;
+        CU(cudaGetLastError());
+        e->cstate ^= 1;
+        return 0;
+    }
+    // sequential kernel only: one copy of the state, in place
+    e->state_ptrs(e->cstate, ca.real_prev, ca.real_hi, ca.bb_hi, ca.bb_last, ca.hi_diverged);
+    cl.redo_only = 0;
+    client_demod_kernel<kDemodThreads><<<cl.nactive, kDemodThreads, smem, cs>>>(ca, cl);
     e->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -1133,7 +1186,7 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
     cl.cpb = e->tail_cpb;
     cl.fchunk = e->demod_fchunk;
     cl.prof = e->d_prof;
-    int rc = launch_demod(e, cab, cl);
+    int rc = (e->opt_client_mask & 1) ? launch_demod(e, cab, cl) : 0;
     if (rc) return rc;
     if (e->banks > 1) {  // the demodulation is the only reader of the spectrum bank
         CU(cudaEventRecord(e->ev_cli[e->cur_bank], cs));
@@ -1144,7 +1197,7 @@ int run_clients(b200_engine *e, uint64_t frame_num, int nframes) {
         CU(cudaStreamWaitEvent(ts, e->ev_demod[buf], 0));
     }
     CU(cudaMemsetAsync(cab.valid, 0, (size_t)e->ca.max_clients * nframes, ts));  // closed slots read back as invalid
-    rc = launch_tail(e, cab, cl);
+    rc = (e->opt_client_mask & 2) ? launch_tail(e, cab, cl) : 0;
     if (rc) return rc;
     if (async_tail) {
         CU(cudaEventRecord(e->ev_tail[buf], ts));
@@ -1231,7 +1284,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax, e->t2.err,
+    void *dev[] = {e->d_redo, e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax, e->t2.err,
                    e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_qtab, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
@@ -1406,6 +1459,11 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_FWD_SUB_FRAMES:
         if (value < 1 || value > 64) return fail(B200_EINVAL, "sub-batch frames must be 1..64");
         e->opt_sub_frames = value;
+        return 0;
+    case B200_OPT_CLIENT_STAGE_MASK: e->opt_client_mask = value & 3; return 0;
+    case B200_OPT_DEMOD_CHUNK:
+        if (value < 0 || value > 64) return fail(B200_EINVAL, "demodulation chunk must be 0 (sequential kernel) .. 64 frames");
+        e->opt_demod_chunk = value;
         return 0;
     case B200_OPT_PCM16:
         if (e->have_clients && !e->use_tail2) return fail(B200_ENOTSUP, "int16 PCM needs the pipelined tail kernel");
@@ -1779,11 +1837,12 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     CU(cudaMalloc((void **)&(ptr), (bytes)));     \
     CU(cudaMemset((ptr), 0, (bytes)))
     ALLOC0(ca.slots, sizeof(ClientSlot) * mc);
-    ALLOC0(ca.real_prev, sizeof(float) * mc * h);
-    ALLOC0(ca.real_hi, sizeof(float) * mc * h);
-    ALLOC0(ca.hi_diverged, sizeof(int) * mc);
-    ALLOC0(ca.bb_hi, sizeof(float2) * mc * h);
-    ALLOC0(ca.bb_last, sizeof(float2) * mc);
+    ALLOC0(ca.real_prev, sizeof(float) * 2 * mc * h);   // two copies: see client_demod_warp_kernel
+    ALLOC0(ca.real_hi, sizeof(float) * 2 * mc * h);
+    ALLOC0(ca.hi_diverged, sizeof(int) * 2 * mc);
+    ALLOC0(ca.bb_hi, sizeof(float2) * 2 * mc * h);
+    ALLOC0(ca.bb_last, sizeof(float2) * 2 * mc);
+    ALLOC0(e->d_redo, mc);
     ALLOC0(ca.dc_x, sizeof(float) * mc * ca.D);
     ALLOC0(ca.dc_m, sizeof(float) * mc * ca.D);
     ALLOC0(ca.dc_sum, sizeof(float) * mc * 2);
@@ -1798,7 +1857,8 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     ALLOC0(ca.valid, 2 * F * mc);
     ALLOC0(e->d_order, sizeof(int) * mc);
     // lane-per-client tail pipeline: state stored [group of 32 slots][...][32]
-    e->use_tail2 = e->opt_tail_pipe && ca.D <= (int)h && ca.L - 1 >= (int)h && tail2_smem(ca.D) <= 200 * 1024;
+    e->use_tail2 = e->opt_tail_pipe && ca.D <= (int)h && ca.L - 1 >= (int)h && tail2_smem(ca.D) <= 200 * 1024 &&
+                   (ca.L - 1 + (int)h - 1) / (int)h >= kT2Depth + 3;  // (suffix maxima are always complete long before they are read)
     if (e->use_tail2) {
         Tail2State &t = e->t2;
         const size_t groups = (mc + 31) / 32;

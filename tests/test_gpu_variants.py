@@ -88,3 +88,57 @@ def test_forward_saturated_soak(gpu_required):
     last = _snapshot(eng, torch, F)
     assert torch.equal(first[0], last[0]) and torch.equal(first[1], last[1])
     eng.close()
+
+
+def test_chunked_demodulation_equals_sequential(gpu_required):
+    """The frame-chunked warp-level demodulation (default) against the sequential one-CTA-per-client kernel: PCM, pwr and
+    valid flags bit-identical for every mode, for chunk sizes that do and do not divide the batch, across batches, across a
+    demodulation switch, and through frames dropped by the NaN guard (src/signal.cpp:266-275: the replay path)."""
+    import torch
+
+    from phantomsdr_b200 import USB, LSB, AM, FM
+    from phantomsdr_b200 import backend as B
+    from phantomsdr_b200.synth import SignalSource, make_clients
+    from helpers import hop_as_floats
+
+    cfg = SpectrumConfig(sps=4_370_000, fft_size=1 << 17)
+    n, h = cfg.audio_fft_size, cfg.audio_fft_size // 2
+    F, nblocks, nc = 16, 4, 41
+    src = SignalSource(cfg, seed=44)
+    specs = make_clients(cfg, nc, modes=(USB, LSB, AM, FM), tones=[src.display_bin(t) for t in src.tones])
+    hops = np.stack([hop_as_floats(src.next_hop()) for _ in range(F * nblocks + 1)])
+    hops[F + 5, 1000:1010] = np.nan   # frames F+4 and F+5 of the stream are dropped for every client
+    results = []
+    for chunk in (0, 8, 5, 1, 64):
+        e = make_engine(cfg)
+        e.set_hop_ring(F * nblocks + 1)
+        e.set_batch_frames(F)
+        e.set_option(B.OPT_DEMOD_CHUNK, chunk)
+        e.clients_create(nc + 1, n, cfg.audio_sps)
+        for i, c in enumerate(specs):
+            e.client_open(i, c.l, c.mid, c.r, c.mode)
+        ring = torch.as_tensor(e.device_hop_ring(F * nblocks + 1), device="cuda")
+        ring.copy_(torch.from_numpy(hops))
+        torch.cuda.synchronize()
+        out = []
+        for k in range(nblocks):
+            if k == 2:
+                e.client_set_demodulation(2, FM)
+                e.client_set_demodulation(7, USB)
+            e.execute_device(k * F, F)
+            e.clients_execute_device(k * F, F)
+            for f in range(F):
+                pcm, pwr, valid = e.clients_fetch(f)
+                out.append((pcm.copy(), pwr.copy(), valid.copy()))
+        results.append(out)
+        e.close()
+    ref = results[0]
+    # frames F+4 and F+5 contain the NaN hop; AM / FM also lose F+6 (its overlap half is the NaN frame's upper half) and FM
+    # F+7 (the discriminator's first step starts from the last sample of F+6)
+    assert not ref[F + 4][2][:nc].any() and not ref[F + 5][2][:nc].any() and ref[F + 8][2][:nc].all(), "NaN frames not dropped"
+    for chunk, res in zip((8, 5, 1, 64), results[1:]):
+        for f, ((pa, wa, va), (pb, wb, vb)) in enumerate(zip(ref, res)):
+            assert np.array_equal(va, vb), f"chunk {chunk} frame {f}: valid flags differ"
+            assert np.array_equal(pa, pb), f"chunk {chunk} frame {f}: PCM differs at clients {np.flatnonzero((pa != pb).any(axis=1))[:8]}"
+            assert np.array_equal(wa.view(np.uint32), wb.view(np.uint32)), f"chunk {chunk} frame {f}: pwr differs"
+    assert any(p.any() for p, _, _ in ref[3 * F:]), "AGC never opened: test is vacuous"
