@@ -227,7 +227,6 @@ def cpu_reference_run(cfg, nclients, frames, warm=1, modes=(AM, USB, LSB), fft_t
 
     oracle.build()
     cores = os.cpu_count() or 1
-    torch.set_num_threads(fft_threads or cores)
     N = cfg.fft_size
     orc = oracle.OracleFFT(N, cfg.downsample_levels, cfg.brightness_offset)
     n = cfg.audio_fft_size
@@ -252,10 +251,14 @@ def cpu_reference_run(cfg, nclients, frames, warm=1, modes=(AM, USB, LSB), fft_t
         a1, a2 = hops[frame % 4], hops[(frame + 1) % 4]
         if cfg.is_real:
             orc.load_real_input(a1, a2)
-            X = torch.fft.rfft(torch.from_numpy(inb))
         else:
             orc.load_complex_input(a1, a2)
-            X = torch.fft.fft(torch.from_numpy(inb).view(torch.complex64))
+        # the thread count is process-wide (torch and the oracle share the OpenMP runtime): restrict it for the FFT only
+        if fft_threads:
+            torch.set_num_threads(fft_threads)
+        X = torch.fft.rfft(torch.from_numpy(inb)) if cfg.is_real else torch.fft.fft(torch.from_numpy(inb).view(torch.complex64))
+        if fft_threads:
+            torch.set_num_threads(cores)
         out[:nfl] = torch.view_as_real(X).reshape(-1).numpy()
         orc.quantize()
         orc.wrap_copy(n)
@@ -269,7 +272,6 @@ def cpu_reference_run(cfg, nclients, frames, warm=1, modes=(AM, USB, LSB), fft_t
     for f in range(frames):
         one(warm + f)
     dt = time.perf_counter() - t0
-    torch.set_num_threads(cores)
     return frames / dt, {"cores": cores, "kind": "port",
                          "sample": f"{frames} frames of the same workload ({nclients} clients); FFT = MKL via torch.fft "
                                    f"(FFTW substitute) on {fft_threads or cores} thread(s), rest = oracle/ C port with OpenMP on "

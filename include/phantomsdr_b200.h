@@ -143,6 +143,10 @@ int b200_set_frame_number(b200_engine *e, uint64_t frame_num);
 #define B200_OPT_DEMOD_CHUNK 19  /* frames per warp task of the frame-chunked demodulation kernel (default 8; 0 = the sequential
                                    one-CTA-per-client kernel only). Results are bit-identical either way. */
 #define B200_OPT_CLIENT_STAGE_MASK 20 /* profiling aid: bit0 = demodulation kernels, bit1 = tail kernel; default 3 */
+#define B200_OPT_FWD_SMS 21      /* SMs the persistent pass-2 kernel sizes its grid for (0 = all): with the tail kernel resident on
+                                  * some SMs a one-CTA-per-SM grid would run in two waves */
+#define B200_OPT_PASS1_SPLIT 22  /* CTAs per column tile of the TMA pass 1 (default 2); more = finer work units for the block scheduler */
+#define B200_OPT_DEMOD_GENERIC 23 /* comparison aid: 1 = run-time-plan demodulation kernel even for audio_fft_size 360 */
 #define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */
 #define B200_OPT_STREAM_LAG1 15  /* ... frame slots between pass 1 and pass 2 of a frame in the item order (default 2) */
 #define B200_OPT_STREAM_LAG2 16  /* ... between pass 1 and the quantiser (default 4) */

@@ -27,6 +27,9 @@ OPT_STREAM_GRID, OPT_STREAM_LAG1, OPT_STREAM_LAG2, OPT_STREAM_RING = 14, 15, 16,
 OPT_PCM16 = 18
 OPT_DEMOD_CHUNK = 19
 OPT_CLIENT_STAGE_MASK = 20
+OPT_FWD_SMS = 21
+OPT_PASS1_SPLIT = 22
+OPT_DEMOD_GENERIC = 23
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 

@@ -93,6 +93,47 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// radix-R butterfly of an inverse (sign +1) DFT, in place; shared by the run-time and the compile-time stage code so that both
+// round identically
+template <int R> __device__ __forceinline__ void butterfly_r(float2 (&a)[R]) {
+    if constexpr (R == 2) {
+        float2 b0 = cadd(a[0], a[1]), b1 = csub(a[0], a[1]);
+        a[0] = b0;
+        a[1] = b1;
+    } else if constexpr (R == 4) {
+        float2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+        float2 t2 = cadd(a[1], a[3]), d = csub(a[1], a[3]);
+        float2 t3 = make_float2(-d.y, d.x);  // +i * d
+        a[0] = cadd(t0, t2);
+        a[1] = cadd(t1, t3);
+        a[2] = csub(t0, t2);
+        a[3] = csub(t1, t3);
+    } else if constexpr (R == 3) {
+        const float hs = 0.86602540378443864676f;
+        float2 sm = cadd(a[1], a[2]), d = csub(a[1], a[2]);
+        float2 m = make_float2(a[0].x - 0.5f * sm.x, a[0].y - 0.5f * sm.y);
+        float2 e = make_float2(-hs * d.y, hs * d.x);
+        a[0] = cadd(a[0], sm);
+        a[1] = cadd(m, e);
+        a[2] = csub(m, e);
+    } else if constexpr (R == 5) {
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
+        float2 t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
+        float2 m1 = make_float2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
+        float2 m2 = make_float2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
+        float2 v1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        float2 v2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        float2 n1 = make_float2(-v1.y, v1.x), n2 = make_float2(-v2.y, v2.x);  // i * v
+        a[0] = make_float2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
+        a[1] = cadd(m1, n1);
+        a[4] = csub(m1, n1);
+        a[2] = cadd(m2, n2);
+        a[3] = csub(m2, n2);
+    }
+}
+
 // One Stockham stage of radix R (sign +1) over `nf` independent transforms stored back to back:
 //   x[t + j*items] -> y[q + s*(R*p + r)],  t = p*s + q,  items = n / R.
 // The whole CTA shares the nf * items butterflies; divisions are multiply-high with host-made constants.
@@ -109,47 +150,61 @@ __device__ __forceinline__ void ifft_stage_fixed(const float2 *xb, float2 *yb, i
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; j++) a[j] = x[t + j * items];
-        if constexpr (R == 2) {
-            float2 b0 = cadd(a[0], a[1]), b1 = csub(a[0], a[1]);
-            a[0] = b0;
-            a[1] = b1;
-        } else if constexpr (R == 4) {
-            float2 t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
-            float2 t2 = cadd(a[1], a[3]), d = csub(a[1], a[3]);
-            float2 t3 = make_float2(-d.y, d.x);  // +i * d
-            a[0] = cadd(t0, t2);
-            a[1] = cadd(t1, t3);
-            a[2] = csub(t0, t2);
-            a[3] = csub(t1, t3);
-        } else if constexpr (R == 3) {
-            const float hs = 0.86602540378443864676f;
-            float2 sm = cadd(a[1], a[2]), d = csub(a[1], a[2]);
-            float2 m = make_float2(a[0].x - 0.5f * sm.x, a[0].y - 0.5f * sm.y);
-            float2 e = make_float2(-hs * d.y, hs * d.x);
-            a[0] = cadd(a[0], sm);
-            a[1] = cadd(m, e);
-            a[2] = csub(m, e);
-        } else if constexpr (R == 5) {
-            const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-            const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-            float2 t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
-            float2 t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
-            float2 m1 = make_float2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
-            float2 m2 = make_float2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
-            float2 v1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-            float2 v2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-            float2 n1 = make_float2(-v1.y, v1.x), n2 = make_float2(-v2.y, v2.x);  // i * v
-            a[0] = make_float2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
-            a[1] = cadd(m1, n1);
-            a[4] = csub(m1, n1);
-            a[2] = cadd(m2, n2);
-            a[3] = csub(m2, n2);
-        }
+        butterfly_r<R>(a);
         const int ob = q + s * R * p;
         y[ob] = a[0];
         const int tw = p * s;  // W_ncur^(p r) = Wn[p*r*s]
 #pragma unroll
         for (int r = 1; r < R; r++) y[ob + s * r] = cmul(a[r], __ldg(Wn + tw * r));
+    }
+}
+
+// The same stage with everything but the lane known at compile time (one transform, one warp): loads and stores are one
+// base address plus immediates, divisions by the stride become multiply-shifts, and the last stage (stride S = N / R, all
+// twiddles 1) skips its multiplies.
+template <int N, int R, int S>
+__device__ __forceinline__ void ifft_stage_static(const float2 *x, float2 *y, const float2 *Wn, int lane) {
+    constexpr int items = N / R;
+    constexpr bool last = (S * R == N);
+#pragma unroll
+    for (int i = 0; i < (items + 31) / 32; i++) {
+        const int t = lane + 32 * i;
+        if ((i + 1) * 32 <= items || t < items) {
+            const int p = (S == 1) ? t : t / S, q = t - p * S;
+            float2 a[R];
+#pragma unroll
+            for (int j = 0; j < R; j++) a[j] = x[t + j * items];
+            butterfly_r<R>(a);
+            float2 *yo = y + (q + S * R * p);
+            yo[0] = a[0];
+            const int tw = p * S;  // W_ncur^(p r) = Wn[p*r*s]
+#pragma unroll
+            for (int r = 1; r < R; r++) yo[S * r] = last ? a[r] : cmul(a[r], __ldg(Wn + tw * r));
+        }
+    }
+    __syncwarp();
+}
+template <int N> struct StaticRadix {  // the host's factorisation order (engine.cu: factorize): 4s, 2s, then odd primes
+    static constexpr int first(int rem) { return rem % 4 == 0 ? 4 : rem % 2 == 0 ? 2 : rem % 3 == 0 ? 3 : rem % 5 == 0 ? 5 : 0; }
+    static constexpr bool ok() {
+        int rem = N;
+        while (rem > 1) {
+            const int r = first(rem);
+            if (!r) return false;
+            rem /= r;
+        }
+        return true;
+    }
+};
+// runs the remaining stages (REM = N / S still to split) and returns the buffer that holds the result
+template <int N, int S, int REM> __device__ __forceinline__ float2 *ifft_static(float2 *x, float2 *y, const float2 *Wn, int lane) {
+    if constexpr (REM == 1) {
+        return x;
+    } else {
+        constexpr int R = StaticRadix<N>::first(REM);
+        static_assert(R != 0, "audio FFT size with a factor other than 2, 3, 5");
+        ifft_stage_static<N, R, S>(x, y, Wn, lane);
+        return ifft_static<N, S * R, REM / R>(y, x, Wn, lane);
     }
 }
 
@@ -371,6 +426,8 @@ __global__ void __launch_bounds__(TPB) client_demod_kernel(const ClientArrays ca
 // ------------------------------------------------------------------------------------------------
 constexpr int kDemodWarps = 8;
 
+// NF: audio FFT size known at compile time (0 = run-time plan from ClientArrays)
+template <int NF>
 __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(const ClientArrays ca, const ClientLaunch cl) {
     extern __shared__ float2 smem_c[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -378,7 +435,7 @@ __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(con
     if (task >= cl.nactive * cl.nchunks) return;
     const int ci = task / cl.nchunks, k = task - ci * cl.nchunks;
     const int slot = cl.order[ci];
-    const int n = ca.n, h = ca.h;
+    const int n = NF ? NF : ca.n, h = NF ? NF / 2 : ca.h;
     float2 *bufX = smem_c + (size_t)warp * (2 * n + h);
     float2 *bufY = bufX + n;
     float2 *prevC = bufY + n;  // overlap state: upper half of the previous frame (SSB: .x only)
@@ -421,6 +478,7 @@ __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(con
     };
     // unnormalised inverse FFT of bufX (signal.cpp:138,154,214); returns the buffer that holds the result
     auto ifft = [&]() -> float2 * {
+        if constexpr (NF != 0) return ifft_static<(NF ? NF : 4), 1, (NF ? NF : 4)>(bufX, bufY, ca.Wn, lane);
         float2 *xb = bufX, *yb = bufY;
         int s = 1;
         for (int st = 0; st < ca.nstages; st++) {

@@ -64,16 +64,21 @@ struct Tail2State {          // device memory, [group] major, 32 clients innermo
     int pcm16;               // 1: PCM rows are int16 (two per 32-bit word), 0: int32 as AudioEncoder::process takes them
 };
 
+// Shared memory of one group of 32 clients: 161 KB with the reference's D = 32 (108 KB at depth 2, measured 5 % slower). (The kernel can run G = 2 groups per CTA,
+// each its own pipeline; the host does not use it - see launch_tail2 in engine.cu for the measurement.)
 __host__ __device__ inline size_t tail2_smem(int D) {
     const size_t nsx = (size_t)D + (kT2Depth + 1) * kT2CH;
-    const size_t ring = sizeof(float) * kT2Depth * kT2CH * kT2Pitch;
-    //        X, M rings                             Y R Dd Old G O   save buffers                    barriers
-    const size_t stg = sizeof(float) * 10 * kT2CH * kT2Pitch;  // staging of the peak (8) and suffix (2) stages
-    return 2 * sizeof(float) * nsx * kT2Pitch + 6 * ring + 2 * sizeof(float) * D * kT2Pitch + stg + 1024;  // 8 edges x 2 x depth mbarriers = 512 B
+    const size_t chunk = sizeof(float) * kT2CH * kT2Pitch;
+    //     X, M rings                                Y R D G rings          out (2 x 2), peak (2 x 2), suffix (2) staging   barriers
+    return 2 * sizeof(float) * nsx * kT2Pitch + 4 * kT2Depth * chunk + 10 * chunk + 1024;
 }
 
-__global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientArrays ca, const ClientLaunch cl, const Tail2State st) {
-    extern __shared__ __align__(16) unsigned char t2_smem[];
+template <int G>
+__global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const ClientArrays ca, const ClientLaunch cl, const Tail2State st,
+                                                                      const int groups) {
+    extern __shared__ __align__(16) unsigned char t2_smem_all[];
+    const int sub = G > 1 ? (int)threadIdx.x / kT2Threads : 0;   // group of this warp inside the CTA
+    unsigned char *t2_smem = t2_smem_all + (size_t)sub * tail2_smem(ca.D);
     const int h = ca.h, D = ca.D, L = ca.L, F = cl.nframes, NB = st.NB;
     const int nsx = st.nsx;
     constexpr int CH = kT2CH, DEPTH = kT2Depth, P = kT2Pitch, NR = kT2Depth * kT2CH;
@@ -82,23 +87,24 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
     float *rY = rM + (size_t)nsx * P;     // DC blocker output
     float *rR = rY + NR * P;               // running maximum of |y| inside the frame
     float *rD = rR + NR * P;               // desired gain
-    float *rO = rD + NR * P;               // delayed sample (front of the look-ahead buffer)
-    float *rG = rO + NR * P;               // gain
-    float *rI = rG + NR * P;               // int16 results (as int), staging of the transposed store
-    float *hX = rI + NR * P;               // [D][P] last D valid inputs of every lane
-    float *hM = hX + (size_t)D * P;        // [D][P] last D valid first-stage averages
-    float *stgP = hM + (size_t)D * P;      // peak stage: [2 warps][2 buffers][old | suffix][CH][P] rows of the look-ahead ring
-    float *stgS = stgP + 8 * CH * P;       // suffix stage: [2 buffers][CH][P]
+    float *rG = rD + NR * P;               // gain
+    float *stgO = rG + NR * P;             // out stage: [2 warps][2 buffers][CH][P] delayed samples (front of the look-ahead
+                                           // buffer) copied straight from the look-ahead ring, turned into int16 results in place
+    float *stgP = stgO + 4 * CH * P;       // peak stage: [2 warps][2 buffers][CH][P] suffix-maximum rows of the look-ahead ring
+    float *stgS = stgP + 4 * CH * P;       // suffix stage: [2 buffers][CH][P]
     uint64_t *bars = reinterpret_cast<uint64_t *>(stgS + 2 * CH * P);
     // edges: 0 X (load -> sum1, sum2)  1 M (sum1 -> sum2)  2 Y (sum2 -> block)  3 R (block -> peak)  4 D (peak -> gain)
-    //        5 O (peak -> out)  6 G (gain -> out)  7 B (block -> suffix, one slot per FRAME)
-    auto full = [&](int e) { return bars + (2 * e) * DEPTH; };
-    auto empty = [&](int e) { return bars + (2 * e + 1) * DEPTH; };
-    __shared__ int s_abort;
-    __shared__ unsigned char s_valid[64][32];   // [frame][lane]: the NaN guard's verdict (src/signal.cpp:266-271)
+    //        5 (unused)  6 G (gain -> out)  7 B (block -> suffix, one slot per FRAME)
+    constexpr int BS = 4;  // barrier slots reserved per edge and direction
+    auto full = [&](int e) { return bars + (2 * e) * BS; };
+    auto empty = [&](int e) { return bars + (2 * e + 1) * BS; };
+    __shared__ int s_abort_all[G];
+    __shared__ unsigned char s_valid_all[G][64][32];   // [frame][lane]: the NaN guard's verdict (src/signal.cpp:266-271)
+    int &s_abort = s_abort_all[sub];
+    unsigned char(*s_valid)[32] = s_valid_all[sub];
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = blockIdx.x;
+    const int tid = (int)threadIdx.x - sub * kT2Threads, warp = tid >> 5, lane = tid & 31;
+    const int grp = (int)blockIdx.x * G + sub;
     const int slot = grp * 32 + lane;
     const bool in_range = slot < ca.max_clients;
     const int flags = in_range ? ca.slots[slot].flags : 0;
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
     if (tid == 0) {
         const int ncons[8] = {2, 1, 1, 1, 1, 1, 1, 1};
         for (int e = 0; e < 8; e++)
-            for (int s = 0; s < DEPTH; s++) {
+            for (int s = 0; s < BS; s++) {
                 mbar_init(full(e) + s, 1);
                 mbar_init(empty(e) + s, ncons[e]);
             }
@@ -120,6 +126,7 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
         s_valid[f][c] = (sl < ca.max_clients && (ca.slots[sl].flags & CF_ACTIVE)) ? ca.valid_a[(size_t)f * ca.max_clients + sl] : 0;
     }
     __syncthreads();
+    if (grp >= groups) return;  // (odd number of groups: the second half of the last CTA)
 
     // bounded waits: a stage that never gets its chunk is a bug in this file - flag it and leave instead of hanging
     auto wait_bar = [&](uint64_t *bar, unsigned parity) -> bool {
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
         }
     };
     // profiling aid (cl.prof != nullptr): cycles the warps of CTA 0 spend waiting for input / for ring space, and in total
-    const bool prof = cl.prof != nullptr && blockIdx.x == 0 && lane == 0;
+    const bool prof = cl.prof != nullptr && grp == 0 && lane == 0;
     long long t_full = 0, t_empty = 0;
     const long long t_start = prof ? clock64() : 0;
 #define T2_WAIT_FULL(e, q)                                                            \
@@ -254,9 +261,10 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
             // A dropped frame pushes nothing: its lane parks the last D inputs (still in the ring when the frame starts)
             // and replays them into the last D positions of the frame, where the next frame will look for them.
             if (!v && active) {
+                float *park = st.dcx + (size_t)grp * D * 32 + lane;  // (read at the start, rewritten at the end: free in between)
                 if (c.a == 0)
-                    for (int i = 0; i < D; i++) hX[i * P + lane] = rX[wrapx(pos + nsx - D + i) * P + lane];
-                for (int j = max(c.a, h - D); j < c.a + c.len; j++) rX[wrapx(pos + (j - c.a)) * P + lane] = hX[(j - (h - D)) * P + lane];
+                    for (int i = 0; i < D; i++) park[i * 32] = rX[wrapx(pos + nsx - D + i) * P + lane];
+                for (int j = max(c.a, h - D); j < c.a + c.len; j++) rX[wrapx(pos + (j - c.a)) * P + lane] = park[(j - (h - D)) * 32];
             }
             T2_SIGNALC(full(0), c);
             pos = wrapx(pos + c.len);
@@ -307,9 +315,10 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
                     ro = wrapx(ro + U);
                 }
             } else if (active) {  // dropped frame: park / replay the last D averages (see the load stage)
+                float *park = st.dcm + (size_t)grp * D * 32 + lane;
                 if (c.a == 0)
-                    for (int i = 0; i < D; i++) hM[i * P + lane] = rM[wrapx(pos + nsx - D + i) * P + lane];
-                for (int j = max(c.a, h - D); j < c.a + len; j++) rM[wrapx(pos + (j - c.a)) * P + lane] = hM[(j - (h - D)) * P + lane];
+                    for (int i = 0; i < D; i++) park[i * 32] = rM[wrapx(pos + nsx - D + i) * P + lane];
+                for (int j = max(c.a, h - D); j < c.a + len; j++) rM[wrapx(pos + (j - c.a)) * P + lane] = park[(j - (h - D)) * 32];
             }
             T2_SIGNALC(full(1), c);
             T2_SIGNALC(empty(0), c);
@@ -421,11 +430,10 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
         const int me = warp - 4;
         int blk = active ? st.blk[g32] : 0;   // block that the frame being processed fills
         int blk_i = blk;                      // ... that the frame whose rows are being requested fills
-        const float *ring = st.ring + (size_t)grp * NB * h * 32 + lane;
         const float *suf = st.suf + (size_t)grp * NB * h * 32 + lane;
         const float *cmx = st.cmax + (size_t)grp * NB * 32 + lane;
         const int kb = st.kb, col0 = st.col0;
-        float *stg = stgP + me * 4 * CH * P + lane;   // [buffer][old | suffix][CH][P]
+        float *stg = stgP + me * 2 * CH * P + lane;   // [buffer][CH][P]
         const int nown = (cpf - me + 1) / 2;          // own chunks per frame: ci = me, me + 2, ...
         const int total = F * nown;
         // rows of the look-ahead ring (delayed samples and their suffix maxima) for own chunk number k: they were written at
@@ -438,21 +446,14 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
                 int c0 = blk_i - kb;
                 if (c0 < 0) c0 += NB;
                 const int c1 = (c0 + 1 == NB) ? 0 : c0 + 1;
-                float *d = stg + (k & 1) * 2 * CH * P;
+                float *d = stg + (k & 1) * CH * P;
                 // the chunk's window ends walk through block c0 from column col0 + a, then through block c1 from column 0
                 const int i0 = col0 + a, n0 = max(0, min(len, h - i0));
-                const float *g0 = ring + ((size_t)c0 * h + i0) * 32, *g1 = ring + ((size_t)c1 * h + (i0 + n0 - h)) * 32;
-                const ptrdiff_t ds = suf - ring;
-#pragma unroll 4
-                for (int j = 0; j < n0; j++) {
-                    cp_async4(d + j * P, g0 + (size_t)j * 32);
-                    cp_async4(d + (CH + j) * P, g0 + ds + (size_t)j * 32);
-                }
-#pragma unroll 4
-                for (int j = n0; j < len; j++) {
-                    cp_async4(d + j * P, g1 + (size_t)(j - n0) * 32);
-                    cp_async4(d + (CH + j) * P, g1 + ds + (size_t)(j - n0) * 32);
-                }
+                const float *g0 = suf + ((size_t)c0 * h + i0) * 32, *g1 = suf + ((size_t)c1 * h + (i0 + n0 - h)) * 32;
+#pragma unroll 8
+                for (int j = 0; j < n0; j++) cp_async4(d + j * P, g0 + (size_t)j * 32);
+#pragma unroll 8
+                for (int j = n0; j < len; j++) cp_async4(d + j * P, g1 + (size_t)(j - n0) * 32);
             }
             cp_async_commit();
             cii += 2;
@@ -489,35 +490,28 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
                 }
             }
             T2_WAIT_EMPTY(4, q);
-            T2_WAIT_EMPTY(5, q);
             if (v) {
-                const float *d = stg + (k & 1) * 2 * CH * P;
+                const float *d = stg + (k & 1) * CH * P;
                 const float *rp = T2_AT(rR, (q % DEPTH) * CH);
                 float *dp = T2_AT(rD, (q % DEPTH) * CH);
-                float *op = T2_AT(rO, (q % DEPTH) * CH);
                 const int nfirst = max(0, min(len, h - (col0 + a)));  // samples whose window end is still in block c0
-                for (int j0 = 0; j0 < len; j0 += U, d += U * P, rp += U * P, dp += U * P, op += U * P) {
+                for (int j0 = 0; j0 < len; j0 += U, d += U * P, rp += U * P, dp += U * P) {
                     if (j0 + U <= len && (j0 + U <= nfirst || j0 >= nfirst)) {
                         const float mid = (j0 < nfirst) ? m0 : m1;
                         float pk[U];
 #pragma unroll
-                        for (int u = 0; u < U; u++) pk[u] = __fadd_rn(fmaxf(fmaxf(d[(CH + u) * P], mid), rp[u * P]), 1e-10f);
+                        for (int u = 0; u < U; u++) pk[u] = __fadd_rn(fmaxf(fmaxf(d[u * P], mid), rp[u * P]), 1e-10f);
 #pragma unroll
-                        for (int u = 0; u < U; u++) {
-                            dp[u * P] = __fdiv_rn(ca.desired, pk[u]);
-                            op[u * P] = d[u * P];
-                        }
+                        for (int u = 0; u < U; u++) dp[u * P] = __fdiv_rn(ca.desired, pk[u]);
                     } else {
                         for (int u = 0; u < U && j0 + u < len; u++) {
                             const float mid = (j0 + u < nfirst) ? m0 : m1;
-                            dp[u * P] = __fdiv_rn(ca.desired, __fadd_rn(fmaxf(fmaxf(d[(CH + u) * P], mid), rp[u * P]), 1e-10f));
-                            op[u * P] = d[u * P];
+                            dp[u * P] = __fdiv_rn(ca.desired, __fadd_rn(fmaxf(fmaxf(d[u * P], mid), rp[u * P]), 1e-10f));
                         }
                     }
                 }
             }
             T2_SIGNAL(full(4), q);
-            T2_SIGNAL(full(5), q);
             T2_SIGNAL(empty(3), q);
             if (ci + 2 >= cpf) {  // last own chunk of the frame
                 if (v && ++blk == NB) blk = 0;
@@ -579,16 +573,54 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
         // (two warps, alternate chunks)
         const int me = warp - 7;
         int since = (active && !reset_agc) ? st.since[g32] : 0;
-        int *tile = reinterpret_cast<int *>(rI) + me * CH * P;
         const unsigned amask = __ballot_sync(0xffffffffu, active);
+        const float *ring = st.ring + (size_t)grp * NB * h * 32 + lane;
+        const int kb = st.kb, col0 = st.col0;
+        float *stg = stgO + me * 2 * CH * P;   // [buffer][CH][P]
+        // The delayed samples of a chunk are rows of the look-ahead ring written at least kb - 1 frames ago: they are
+        // requested one own chunk ahead, independent of every other stage.
+        auto advance = [&](ChunkIt &x, int &b) {  // next chunk; b = look-ahead block that x's frame fills
+            const int f0 = x.f;
+            chunk_next(x);
+            if (x.f != f0 && valid_of(f0) && ++b == NB) b = 0;
+        };
+        auto request = [&](const ChunkIt &x, int b, int buf) {
+            if (valid_of(x.f)) {
+                int c0 = b - kb;
+                if (c0 < 0) c0 += NB;
+                const int c1 = (c0 + 1 == NB) ? 0 : c0 + 1;
+                float *d = stg + buf * CH * P + lane;
+                const int i0 = col0 + x.a, n0 = max(0, min(x.len, h - i0));
+                const float *g0 = ring + ((size_t)c0 * h + i0) * 32, *g1 = ring + ((size_t)c1 * h + (i0 + n0 - h)) * 32;
+#pragma unroll 8
+                for (int j = 0; j < n0; j++) cp_async4(d + j * P, g0 + (size_t)j * 32);
+#pragma unroll 8
+                for (int j = n0; j < x.len; j++) cp_async4(d + j * P, g1 + (size_t)(j - n0) * 32);
+            }
+            cp_async_commit();
+        };
+        int blk = active ? st.blk[g32] : 0;
         ChunkIt c = chunk_first();
-        for (int q = 0; q < nq; q++, chunk_next(c)) {
+        ChunkIt cn = c;   // the own chunk whose rows are requested next
+        int blk_n = blk, qn = 0, k = 0;
+        for (; qn < me && qn < nq - 1; qn++) advance(cn, blk_n);
+        if (me < nq) request(cn, blk_n, 0);
+        for (int q = 0; q < nq; q++) {
             const int f = c.f, a = c.a, len = c.len;
             const bool v = valid_of(f);
             if ((q & 1) == me) {
-                T2_WAITC_FULL(5, c);
+                if (q + 2 < nq) {
+                    advance(cn, blk_n);
+                    advance(cn, blk_n);
+                    request(cn, blk_n, (k + 1) & 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
                 T2_WAITC_FULL(6, c);
-                const float *op = T2_AT(rO, c.slot * CH);
+                int *tile = reinterpret_cast<int *>(stg + (k & 1) * CH * P);  // results replace the delayed samples in place
+                k++;
+                const float *op = reinterpret_cast<const float *>(tile) + lane;
                 const float *gp = T2_AT(rG, c.slot * CH);
                 int *tp = tile + lane;
                 const int first = v ? max(0, min(len, L - 1 - since - a)) : len;
@@ -616,7 +648,6 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
                         }
                     }
                 }
-                T2_SIGNALC(empty(5), c);
                 T2_SIGNALC(empty(6), c);
                 __syncwarp();
                 // one client row at a time, lanes along the samples of the chunk
@@ -648,6 +679,7 @@ __global__ void __launch_bounds__(kT2Threads) client_tail2_kernel(const ClientAr
                 if (active && ((f & 1) == me)) ca.valid[(size_t)f * ca.max_clients + slot] = v ? 1 : 0;
                 if (v) since = min(since + h, L);
             }
+            if (q + 1 < nq) chunk_next(c);
         }
     } else {
         // ================= suffix: in-block suffix maxima of |y| for every finished block =================

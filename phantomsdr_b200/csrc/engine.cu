@@ -194,6 +194,8 @@ struct b200_engine {
     int opt_tail_pipe = 1;
     int opt_packed = 1;                 // bit0: packed-f32 (FMUL2/FADD2) waterfall quantiser
     int opt_pass1_order = 0;            // item order of the TMA pass 1 (see fft_pass1_tma_kernel)
+    int opt_fwd_sms = 0;                // SMs the persistent forward kernels size their grids for (0 = all)
+    int opt_p1_split = 2;               // CTAs per column tile of the TMA pass 1 (frames f == part mod split)
     int opt_lanes = 1;                  // forward lanes: sub-batches of a batch run on this many streams
     int opt_sub_frames = 64;            // frames per sub-batch (>= batch: one launch group per batch)
     cudaStream_t lane_stream[4] = {};
@@ -249,6 +251,7 @@ struct b200_engine {
     int demod_fchunk = 1;
     int opt_client_mask = 3;            // profiling aid: bit0 = demodulation kernels, bit1 = tail kernel
     int opt_demod_chunk = 8;            // frames per warp task of the frame-chunked demodulation (0 = sequential kernel only)
+    int opt_demod_generic = 0;          // 1: never use the compile-time-size demodulation kernel (comparison aid)
     int demod_wpc = 0;                  // warps per CTA of client_demod_warp_kernel (0 = audio FFT too long: sequential kernel)
     int cstate = 0;                     // which copy of the overlap state the next client batch reads
     unsigned char *d_redo = nullptr;
@@ -486,7 +489,7 @@ int tma_ring_map(b200_engine *e) {  // whenever the hop ring is (re)allocated
 int launch_tma_pass1(b200_engine *e, const FwdParams &p, int frames) {
     // order 0: two CTAs share a column tile (even / odd frames); 1 / 2: equal chunks of the tile- / frame-major item list
     const int order = e->opt_pass1_order;
-    const int nsplit = frames >= 2 ? 2 : 1;
+    const int nsplit = std::max(1, std::min(e->opt_p1_split, frames));
     const int grid = order == 0 ? (kS / kTmaT) * nsplit : std::min((kS / kTmaT) * frames, 2 * e->num_sms);
     if (e->is_real)
         fft_pass1_tma_kernel<true><<<grid, kTmaThreads, TmaSmem::kPass1R, e->stream>>>(p, e->ring_map, e->window_map, frames,
@@ -501,7 +504,7 @@ int launch_tma_pass1(b200_engine *e, const FwdParams &p, int frames) {
 int launch_tma_pass2(b200_engine *e, const FwdParams &p, int frames, int fuse, const PyrParams *pyr = nullptr, int lane = 0) {
     const int total = (kS / kTmaT) * frames;
     if (e->opt_tma >= 2 && fuse != 1) {  // three-stage variant: one CTA of two consumer groups per SM
-        const int grid = std::min(total, e->num_sms);
+        const int grid = std::min(total, e->opt_fwd_sms > 0 ? std::min(e->opt_fwd_sms, e->num_sms) : e->num_sms);
         const bool peers = p.npeers > 0;
         PyrParams none{};
         if (pyr) {  // spectrum + whole pyramid in one launch (FUSE 3): zero the per-frame tile counters first
@@ -1051,7 +1054,10 @@ int launch_demod(b200_engine *e, const ClientArrays &ca_in, const ClientLaunch &
         CU(cudaFuncSetAttribute(client_demod_kernel<kDemodThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         e->demod_wpc = (int)std::min<size_t>(kDemodWarps, (200 * 1024) / per_warp);
         if (e->demod_wpc >= 1)
-            CU(cudaFuncSetAttribute(client_demod_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * e->demod_wpc)));
+        {
+            CU(cudaFuncSetAttribute(client_demod_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * e->demod_wpc)));
+            CU(cudaFuncSetAttribute(client_demod_warp_kernel<360>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * e->demod_wpc)));
+        }
         return 0;
     }
     cudaStream_t cs = e->client_stream();
@@ -1075,7 +1081,10 @@ int launch_demod(b200_engine *e, const ClientArrays &ca_in, const ClientLaunch &
         cl.redo_only = 0;
         CU(cudaMemsetAsync(e->d_redo, 0, (size_t)e->ca.max_clients, cs));
         const int tasks = cl.nactive * cl.nchunks;
-        client_demod_warp_kernel<<<(tasks + e->demod_wpc - 1) / e->demod_wpc, 32 * e->demod_wpc, per_warp * e->demod_wpc, cs>>>(ca, cl);
+        const dim3 grid((tasks + e->demod_wpc - 1) / e->demod_wpc), block(32 * e->demod_wpc);
+        // 360 = the reference's audio FFT size at 12 kHz audio and the headline frame rate: stages unrolled at compile time
+        if (e->ca.n == 360 && !e->opt_demod_generic) client_demod_warp_kernel<360><<<grid, block, per_warp * e->demod_wpc, cs>>>(ca, cl);
+        else client_demod_warp_kernel<0><<<grid, block, per_warp * e->demod_wpc, cs>>>(ca, cl);
         e->launches++;
         CU(cudaGetLastError());
         cl.redo_only = 1;
@@ -1106,13 +1115,17 @@ template <int KB> int launch_tail_kb(b200_engine *e, const ClientArrays &ca, con
     return 0;
 }
 int launch_tail2(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
-    const size_t smem = tail2_smem(e->ca.D);
+    // One group of 32 clients per CTA, and the CTA asks for (nearly) all the shared memory of its SM although it needs
+    // about half: every stage of the pipeline is a single warp on the critical path, and warps of other CTAs competing
+    // for the SM's issue slots slow the whole chain. Measured at 1024 clients beside the forward kernels: two groups
+    // per SM (as two CTAs or as one CTA of 20 warps) 16.9 us/frame of tails and 23-26 GS/s, one group per SM 11.3 and 31.
+    const size_t smem = std::max(tail2_smem(e->ca.D), (size_t)200 * 1024);
     if (cl.nactive == 0) {  // preparation call from clients_create
-        CU(cudaFuncSetAttribute(client_tail2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
     }
     const int groups = (e->ca.max_clients + 31) / 32;
-    client_tail2_kernel<<<groups, kT2Threads, smem, e->tail_stream()>>>(ca, cl, e->t2);
+    client_tail2_kernel<1><<<groups, kT2Threads, smem, e->tail_stream()>>>(ca, cl, e->t2, groups);
     e->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(e->h_tail_err, e->t2.err, sizeof(int), cudaMemcpyDeviceToHost, e->tail_stream()));
@@ -1459,6 +1472,15 @@ int b200_set_option(b200_engine *e, int option, int value) {
     case B200_OPT_FWD_SUB_FRAMES:
         if (value < 1 || value > 64) return fail(B200_EINVAL, "sub-batch frames must be 1..64");
         e->opt_sub_frames = value;
+        return 0;
+    case B200_OPT_DEMOD_GENERIC: e->opt_demod_generic = value ? 1 : 0; return 0;
+    case B200_OPT_FWD_SMS:
+        if (value < 0 || value > 1024) return fail(B200_EINVAL, "forward SM count must be 0 (all) .. 1024");
+        e->opt_fwd_sms = value;
+        return 0;
+    case B200_OPT_PASS1_SPLIT:
+        if (value < 1 || value > 64) return fail(B200_EINVAL, "pass-1 split must be 1..64");
+        e->opt_p1_split = value;
         return 0;
     case B200_OPT_CLIENT_STAGE_MASK: e->opt_client_mask = value & 3; return 0;
     case B200_OPT_DEMOD_CHUNK:
@@ -1857,7 +1879,7 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
     ALLOC0(ca.valid, 2 * F * mc);
     ALLOC0(e->d_order, sizeof(int) * mc);
     // lane-per-client tail pipeline: state stored [group of 32 slots][...][32]
-    e->use_tail2 = e->opt_tail_pipe && ca.D <= (int)h && ca.L - 1 >= (int)h && tail2_smem(ca.D) <= 200 * 1024 &&
+    e->use_tail2 = e->opt_tail_pipe && ca.D <= (int)h && ca.L - 1 >= (int)h && tail2_smem(ca.D) <= 220 * 1024 &&
                    (ca.L - 1 + (int)h - 1) / (int)h >= kT2Depth + 3;  // (suffix maxima are always complete long before they are read)
     if (e->use_tail2) {
         Tail2State &t = e->t2;

@@ -3,7 +3,7 @@ import sys
 sys.path.insert(0, '.')
 import torch
 from phantomsdr_b200 import SpectrumConfig, AM, USB, LSB
-from phantomsdr_b200.backend import B200FFT, OPT_DEMOD_CHUNK, OPT_CLIENT_STAGE_MASK
+from phantomsdr_b200.backend import B200FFT, OPT_DEMOD_CHUNK, OPT_CLIENT_STAGE_MASK, OPT_DEMOD_GENERIC
 from phantomsdr_b200.synth import make_clients
 
 NC = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
@@ -41,8 +41,10 @@ def t(reps=10):
     return a.elapsed_time(b) * 1e3 / (reps * F)
 
 
-for name, mask, chunk in (("demod sequential", 1, 0), ("demod chunk 4", 1, 4), ("demod chunk 8", 1, 8), ("demod chunk 16", 1, 16),
-                          ("demod chunk 32", 1, 32), ("tails", 2, 8), ("demod chunk 8 + tails", 3, 8)):
+for name, mask, chunk, gen in (("demod sequential", 1, 0, 0), ("demod chunk 8 run-time plan", 1, 8, 1), ("demod chunk 4", 1, 4, 0),
+                               ("demod chunk 8", 1, 8, 0), ("demod chunk 16", 1, 16, 0), ("demod chunk 32", 1, 32, 0),
+                               ("tails", 2, 8, 0), ("demod chunk 8 + tails", 3, 8, 0)):
     eng.set_option(OPT_CLIENT_STAGE_MASK, mask)
     eng.set_option(OPT_DEMOD_CHUNK, chunk)
+    eng.set_option(OPT_DEMOD_GENERIC, gen)
     print(f"{NC} clients, batch {F}: {name:24s} {t():7.2f} us/frame", flush=True)
