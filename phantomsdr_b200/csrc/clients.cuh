@@ -428,7 +428,7 @@ constexpr int kDemodWarps = 8;
 
 // NF: audio FFT size known at compile time (0 = run-time plan from ClientArrays)
 template <int NF>
-__global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(const ClientArrays ca, const ClientLaunch cl) {
+__global__ void __launch_bounds__(32 * kDemodWarps, 3) client_demod_warp_kernel(const ClientArrays ca, const ClientLaunch cl) {
     extern __shared__ float2 smem_c[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int task = blockIdx.x * (blockDim.x >> 5) + warp;  // (fewer than kDemodWarps warps per CTA for very long audio FFTs)
@@ -475,6 +475,48 @@ __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(con
             bufX[kk] = v;
         }
         __syncwarp();
+    };
+    // The same placement for a compile-time n, reading the slice ONCE: all loads of the lane are issued together (the slice
+    // is at most n bins = (n + 31) / 32 per lane), the slice power is summed from the registers in the order of the loop
+    // above (lane-strided, then the warp reduction), and every bin is then scattered to its place(s) in the zeroed input.
+    auto load_place = [&](int f, bool want_pw) -> float {
+        constexpr int NI = NF ? (NF + 31) / 32 : 1, NB = 6;  // NB loads in flight per lane (registers)
+        const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+            if (lane + 32 * i < n) bufX[lane + 32 * i] = make_float2(0.f, 0.f);
+        __syncwarp();
+        float pw = 0.f;
+#pragma unroll
+        for (int i0 = 0; i0 < NI; i0 += NB) {
+            float2 v[NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const int idx = lane + 32 * (i0 + i);
+                v[i] = (i0 + i < NI && idx < len) ? buf[idx] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const int idx = lane + 32 * (i0 + i);
+                if (i0 + i < NI && idx < len) {
+                    const float2 x = v[i];
+                    if (want_pw) pw += x.x * x.x + x.y * x.y;
+                    if (ssb) {
+                        const int k2 = (mode == MODE_USB) ? idx - audio_m : audio_m - idx;
+                        if (k2 >= 0 && k2 <= n / 2) {
+                            const bool edge = (k2 == 0 || k2 == n / 2);  // c2r ignores Im of DC / Nyquist
+                            bufX[k2] = make_float2(x.x, edge ? 0.f : x.y);
+                            if (!edge) bufX[n - k2] = make_float2(x.x, -x.y);  // Hermitian mirror
+                        }
+                    } else {
+                        const int d = idx - audio_m;  // positive bins [0, n/2), negative [-n/2+1, -1]
+                        if (d > -n / 2 && d < n / 2) bufX[d >= 0 ? d : d + n] = x;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        return want_pw ? warp_sum(pw) : 0.f;
     };
     // unnormalised inverse FFT of bufX (signal.cpp:138,154,214); returns the buffer that holds the result
     auto ifft = [&]() -> float2 * {
@@ -525,7 +567,8 @@ __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(con
         float2 hi2 = make_float2(0.f, 0.f);  // upper-half sample h - 1 of frame f_begin - 2, as frame f_begin - 1 overlapped it
         if (mode == MODE_FM) {
             if (f_begin >= 2) {
-                gather(f_begin - 2);
+                if constexpr (NF != 0) load_place(f_begin - 2, false);
+                else gather(f_begin - 2);
                 const float2 *x = ifft();
                 const float sg = sign_of(f_begin - 2);
                 hi2 = make_float2(sg * x[n - 1].x, sg * x[n - 1].y);
@@ -534,7 +577,8 @@ __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(con
                 hi2 = cl.sin_bb_hi[(size_t)slot * h + h - 1];
             }
         }
-        gather(f_begin - 1);
+        if constexpr (NF != 0) load_place(f_begin - 1, false);
+        else gather(f_begin - 1);
         const float2 *x = ifft();
         const float sg = sign_of(f_begin - 1);
         if (!ssb) last = make_float2(__fadd_rn(sg * x[h - 1].x, hi2.x), __fadd_rn(sg * x[h - 1].y, hi2.y));
@@ -543,14 +587,18 @@ __global__ void __launch_bounds__(32 * kDemodWarps) client_demod_warp_kernel(con
 
     // ---- the task's own frames, in order ----
     for (int f = f_begin; f < f_end; f++) {
-        const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
         float pw = 0.f;  // slice power (signal.cpp:117-119)
-        for (int i = lane; i < len; i += 32) {
-            const float2 v = buf[i];
-            pw += v.x * v.x + v.y * v.y;
+        if constexpr (NF != 0) {
+            pw = load_place(f, true);
+        } else {
+            const float2 *buf = cl.spec + (size_t)f * cl.spec_stride + off;
+            for (int i = lane; i < len; i += 32) {
+                const float2 v = buf[i];
+                pw += v.x * v.x + v.y * v.y;
+            }
+            pw = warp_sum(pw);
+            gather(f);
         }
-        pw = warp_sum(pw);
-        gather(f);
         float2 *x = ifft();
         float2 *y = (x == bufX) ? bufY : bufX;  // free scratch
         const float sg = sign_of(f);
