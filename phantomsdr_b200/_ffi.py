@@ -9,6 +9,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "lib" / "libphantomsdr_b200.so"
 HEADER = PKG.parent / "include" / "phantomsdr_b200.h"
+DEBUG_HEADER = PKG.parent / "include" / "phantomsdr_b200_debug.h"  # tuning knobs, profiling hooks
 
 _vp, _sz, _i, _d, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_uint64
 _pp = C.POINTER(C.c_void_p)
@@ -30,6 +31,7 @@ SIGNATURES = {
     "b200_load_complex_input": (_i, [_vp, _vp, _vp]),
     "b200_execute": (_i, [_vp]),
     "b200_set_option": (_i, [_vp, _i, _i]),
+    "b200_debug_option": (_i, [_vp, _i, _i]),
     "b200_load_raw_input": (_i, [_vp, _vp, _vp]),
     "b200_device_spectrum": (_vp, [_vp]),
     "b200_device_quantized": (_vp, [_vp]),

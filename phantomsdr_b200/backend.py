@@ -30,6 +30,7 @@ OPT_CLIENT_STAGE_MASK = 20
 OPT_FWD_SMS = 21
 OPT_PASS1_SPLIT = 22
 OPT_DEMOD_GENERIC = 23
+_PUBLIC_OPTIONS = {OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_PEER_STORES, OPT_PCM16}  # include/phantomsdr_b200.h
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 
 
@@ -138,7 +139,11 @@ class B200FFT:
         return 0
 
     def set_option(self, option: int, value: int) -> None:
-        check(self.L.b200_set_option(self.h, option, value))
+        """Engine options go through b200_set_option, tuning knobs (phantomsdr_b200_debug.h) through b200_debug_option."""
+        if option in _PUBLIC_OPTIONS:
+            check(self.L.b200_set_option(self.h, option, value))
+        else:
+            check(self.L.b200_debug_option(self.h, option, value))
 
     def set_waterfall_cadence(self, skip_num: int) -> None:
         """Pyramids only for frames with frame_num % skip_num == 0 (src/fft.cpp:33,102-104)."""

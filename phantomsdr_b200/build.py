@@ -34,7 +34,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*")) + [PKG.parent / "include" / "phantomsdr_b200.h", Path(__file__)]
+    deps = list(CSRC.glob("*")) + list((PKG.parent / "include").glob("*.h")) + [Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 

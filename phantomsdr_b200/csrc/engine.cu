@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/phantomsdr_b200.h"
+#include "../../include/phantomsdr_b200_debug.h"
 #include "clients.cuh"
 #include "clients_tail.cuh"
 #include "fft_fwd.cuh"
@@ -956,7 +957,7 @@ int plan_common(b200_engine *e, bool is_real) {
     if (const char *opts = getenv("B200_OPTS")) {  // tuning aid: "option=value,option=value" applied after planning
         int k = 0, v = 0, used = 0;
         while (sscanf(opts, "%d=%d%n", &k, &v, &used) == 2) {
-            b200_set_option(e, k, v);
+            b200_debug_option(e, k, v);
             opts += used;
             if (*opts == ',') opts++;
         }
@@ -1429,6 +1430,17 @@ int b200_load_raw_input(b200_engine *e, const void *a1, const void *a2) {
 }
 
 int b200_set_option(b200_engine *e, int option, int value) {
+    switch (option) {
+    case B200_OPT_RELOAD_BOTH:
+    case B200_OPT_HOST_MIRROR:
+    case B200_OPT_INPUT_FORMAT:
+    case B200_OPT_PEER_STORES:
+    case B200_OPT_PCM16: return b200_debug_option(e, option, value);
+    default: return fail(B200_EINVAL, "unknown option %d (tuning knobs: b200_debug_option, phantomsdr_b200_debug.h)", option);
+    }
+}
+
+int b200_debug_option(b200_engine *e, int option, int value) {
     if (!e) return fail(B200_EINVAL, "null engine");
     switch (option) {
     case B200_OPT_RELOAD_BOTH: e->opt_reload_both = value ? 1 : 0; return 0;

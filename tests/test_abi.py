@@ -11,9 +11,17 @@ from phantomsdr_b200 import _ffi
 
 
 def header_symbols():
-    text = _ffi.HEADER.read_text()
+    # the drop-in boundary plus the tuning / profiling header: every include/*.h declaration must be exported
+    text = _ffi.HEADER.read_text() + _ffi.DEBUG_HEADER.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_tuning_knobs_are_not_part_of_the_boundary():
+    public = re.sub(r"/\*.*?\*/", "", _ffi.HEADER.read_text(), flags=re.S)
+    opts = set(re.findall(r"#define (B200_OPT_[A-Z0-9_]+)", public))
+    assert opts == {"B200_OPT_RELOAD_BOTH", "B200_OPT_HOST_MIRROR", "B200_OPT_INPUT_FORMAT", "B200_OPT_PEER_STORES", "B200_OPT_PCM16"}
+    assert "b200_debug" not in public
 
 
 def test_library_built_in_tree():

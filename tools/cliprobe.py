@@ -42,7 +42,8 @@ def t(reps=10):
 
 
 for name, mask, chunk, gen in (("demod sequential", 1, 0, 0), ("demod chunk 8 run-time plan", 1, 8, 1), ("demod chunk 4", 1, 4, 0),
-                               ("demod chunk 8", 1, 8, 0), ("demod chunk 16", 1, 16, 0), ("demod chunk 32", 1, 32, 0),
+                               ("demod chunk 7", 1, 7, 0), ("demod chunk 8", 1, 8, 0), ("demod chunk 10", 1, 10, 0), ("demod chunk 11", 1, 11, 0),
+                               ("demod chunk 16", 1, 16, 0), ("demod chunk 32", 1, 32, 0),
                                ("tails", 2, 8, 0), ("demod chunk 8 + tails", 3, 8, 0)):
     eng.set_option(OPT_CLIENT_STAGE_MASK, mask)
     eng.set_option(OPT_DEMOD_CHUNK, chunk)
