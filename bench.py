@@ -721,10 +721,13 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
             breakdown["cufft_bare_transform_us_per_frame"] = f"unavailable: {exc!r}"
         traffic, traffic_src = None, None
         try:
-            tr = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
-            if tr.get("batch") == F and tr.get("is_real") == cfg.is_real and tr.get("fft_log2") == args.fft_log2:
-                traffic = tr["dram_bytes_per_launch_group"]
-                traffic_src = tr.get("source")
+            # measured once per kernel change with ncu --set full (tools/gpu_profile_pack2.sh, tools/ncu_summary.py traffic);
+            # the file names the build it was taken from
+            for name in ("r2_traffic.json", "r2_traffic_r2c.json"):
+                tr = json.loads((ROOT / "profiles" / name).read_text())
+                if tr.get("batch") == F and tr.get("is_real") == cfg.is_real and tr.get("fft_log2") == args.fft_log2:
+                    traffic = tr["dram_bytes_per_launch_group"]
+                    traffic_src = tr.get("source")
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": "forward FFT + waterfall (fft_pass1 + fft_pass2 + pyramid, one launch each per "

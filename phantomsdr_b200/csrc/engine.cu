@@ -252,6 +252,7 @@ struct b200_engine {
     int demod_fchunk = 1;
     int opt_client_mask = 3;            // profiling aid: bit0 = demodulation kernels, bit1 = tail kernel
     int opt_demod_chunk = 8;            // frames per warp task of the frame-chunked demodulation (0 = sequential kernel only)
+    int flag_waits = 0;                 // b200_enqueue_wait calls since stream_check last read the flag error word
     int opt_demod_generic = 0;          // 1: never use the compile-time-size demodulation kernel (comparison aid)
     int demod_wpc = 0;                  // warps per CTA of client_demod_warp_kernel (0 = audio FFT too long: sequential kernel)
     int cstate = 0;                     // which copy of the overlap state the next client batch reads
@@ -650,6 +651,12 @@ int stream_check(b200_engine *e) {
     if (e->h_tail_err && *e->h_tail_err)
         return fail(B200_ECUDA, "client tail pipeline: a bounded wait expired (protocol timeout, code %d = 10000 + 100 * stage + barrier); "
                                 "results of the batch are incomplete", *e->h_tail_err);
+    if (e->flag_waits && e->d_flag_err) {  // stream-ordered peer flags were waited on since the last check
+        int v = 0;
+        if (cudaMemcpy(&v, e->d_flag_err, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && v)
+            return fail(B200_ECUDA, "a peer flag wait timed out (b200_enqueue_wait): the peer's data did not arrive");
+        e->flag_waits = 0;
+    }
     return 0;
 }
 
@@ -1771,11 +1778,12 @@ int b200_enqueue_wait(b200_engine *e, int client_stream, void *const *flag_ptrs,
     int rc = flag_list(e, flag_ptrs, n, &fl);
     if (rc) return rc;
     CU(cudaSetDevice(e->device));
-    const long long cycles = (long long)timeout_ms * 1900000ll;  // ~1.9 GHz SM clock
+    const unsigned long long timeout_ns = (unsigned long long)std::max(1, timeout_ms) * 1000000ull;
     cudaStream_t st;
     rc = pick_stream(e, client_stream, &st);
     if (rc) return rc;
-    flag_wait_kernel<<<1, 32, 0, st>>>(fl, min_value, cycles, e->d_flag_err);
+    flag_wait_kernel<<<1, 32, 0, st>>>(fl, min_value, timeout_ns, e->d_flag_err);
+    e->flag_waits++;
     e->launches++;
     CU(cudaGetLastError());
     return 0;

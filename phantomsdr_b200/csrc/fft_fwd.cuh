@@ -723,7 +723,9 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
     pyramid_tree<PER, PK, TB>(p, frame, blk, tid, pw, B, warp_sum_s, sync);
 }
 
-template <int MODE, int PER, bool PK, bool TB = false> __global__ void __launch_bounds__(256) pyramid_kernel(const PyrParams p) {
+// (the Hermitian-split mode is bound by the latency of its mirrored loads: three CTAs per SM instead of the two its 82 registers allow)
+template <int MODE, int PER, bool PK, bool TB = false>
+__global__ void __launch_bounds__(256, MODE == PYR_R2C ? 3 : 1) pyramid_kernel(const PyrParams p) {
     __shared__ float warp_sum_s[8];
     pyramid_block<MODE, PER, PK, false, TB>(p, p.frame0 + (int)blockIdx.y * p.frame_step, blockIdx.x, threadIdx.x, warp_sum_s, CtaSync{});
 }
@@ -773,13 +775,19 @@ __global__ void flag_signal_kernel(FlagList fl, unsigned long long value) {
         __threadfence_system();
     }
 }
-// spins until every flag >= min_value; gives up after timeout_cycles (sets *err) so a lost peer cannot hang the GPU
-__global__ void flag_wait_kernel(FlagList fl, unsigned long long min_value, long long timeout_cycles, int *err) {
+// spins until every flag >= min_value; gives up after timeout_ns of wall time (%globaltimer; sets *err) so a lost peer
+// cannot hang the GPU
+__global__ void flag_wait_kernel(FlagList fl, unsigned long long min_value, unsigned long long timeout_ns, int *err) {
     if (threadIdx.x < fl.n) {
-        const long long t0 = clock64();
+        auto now_ns = [] {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            return t;
+        };
+        const unsigned long long t0 = now_ns();
         volatile unsigned long long *f = reinterpret_cast<volatile unsigned long long *>(fl.ptr[threadIdx.x]);
         while (*f < min_value) {
-            if (clock64() - t0 > timeout_cycles) {
+            if (now_ns() - t0 > timeout_ns) {
                 *err = 1;
                 break;
             }

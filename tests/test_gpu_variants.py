@@ -40,7 +40,8 @@ def test_forward_variants_bit_identical(gpu_required):
     F = 8
     eng, torch, B = _device_engine(cfg, F, 12)
     defaults = {B.OPT_FUSED_PYRAMID: -1, B.OPT_TMA: 2, B.OPT_PACKED_MATH: 1, B.OPT_FWD_LANES: 1, B.OPT_FWD_SUB_FRAMES: 64,
-                B.OPT_PASS1_ORDER: 0, B.OPT_PYRAMID_LAG: 2}
+                B.OPT_PASS1_ORDER: 0, B.OPT_PYRAMID_LAG: 2, B.OPT_PASS1_SPLIT: 2, B.OPT_FWD_SMS: 0, B.OPT_STREAM_LAG1: 2,
+                B.OPT_STREAM_LAG2: 4, B.OPT_STREAM_RING: 5}
     variants = [
         {},
         {B.OPT_PACKED_MATH: 0},
@@ -58,6 +59,11 @@ def test_forward_variants_bit_identical(gpu_required):
         {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 3},
         {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 8},          # lag >= frames: every block is produced by the tail loop
         {B.OPT_TMA: 3, B.OPT_FWD_LANES: 2, B.OPT_FWD_SUB_FRAMES: 2},
+        {B.OPT_PASS1_SPLIT: 8},                        # finer pass-1 work units
+        {B.OPT_FWD_SMS: 100},                          # pass-2 grid sized for fewer SMs
+        {B.OPT_PACKED_MATH: 3},                        # table-driven quantiser for levels 0..2
+        {B.OPT_TMA: 4},                                # all three stages in one persistent dataflow-scheduled launch
+        {B.OPT_TMA: 4, B.OPT_STREAM_LAG1: 1, B.OPT_STREAM_LAG2: 2, B.OPT_STREAM_RING: 3},
     ]
     ref = None
     for opts in variants:
@@ -68,10 +74,14 @@ def test_forward_variants_bit_identical(gpu_required):
             ref = (spec, quant)
             assert float(spec.abs().max()) > 0
             continue
-        if opts.get(B.OPT_TMA, 2) == 0:
-            # the generic kernels share the arithmetic but not the instruction order of the twiddle products
+        if opts.get(B.OPT_TMA, 2) in (0, 4):
+            # the generic and the stream kernels share the arithmetic but not the instruction order / contraction of the
+            # twiddle products: spectrum to rounding, int8 values off by one only where a power sits on a quantiser step
             err = float((spec - ref[0]).abs().max()) / float(ref[0].abs().max())
             assert err <= 1e-5, f"{opts}: spectrum differs by {err:.2e}"
+            dq = (quant.to(torch.int16) - ref[1].to(torch.int16)).abs()
+            dq = torch.minimum(dq, 256 - dq)  # (the reference's int8 wrap)
+            assert int(dq.max()) <= 1 and float((dq != 0).float().mean()) <= 1e-4, f"{opts}: pyramid differs"
             continue
         assert torch.equal(spec, ref[0]), f"{opts}: spectrum not bit-identical"
         assert torch.equal(quant, ref[1]), f"{opts}: pyramid not bit-identical"
