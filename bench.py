@@ -721,7 +721,7 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
             breakdown["cufft_bare_transform_us_per_frame"] = f"unavailable: {exc!r}"
         traffic, traffic_src = None, None
         try:
-            # measured once per kernel change with ncu --set full (tools/gpu_profile_pack2.sh, tools/ncu_summary.py traffic);
+            # measured once per kernel change with ncu --set full (tools/gpu_profile_pack.sh, tools/ncu_summary.py traffic);
             # the file names the build it was taken from
             for name in ("r2_traffic.json", "r2_traffic_r2c.json"):
                 tr = json.loads((ROOT / "profiles" / name).read_text())
