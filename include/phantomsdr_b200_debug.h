@@ -34,6 +34,7 @@ extern "C" {
                                   * some SMs a one-CTA-per-SM grid would run in two waves */
 #define B200_OPT_PASS1_SPLIT 22  /* CTAs per column tile of the TMA pass 1 (default 2); more = finer work units for the block scheduler */
 #define B200_OPT_DEMOD_GENERIC 23 /* comparison aid: 1 = run-time-plan demodulation kernel even for audio_fft_size 360 */
+#define B200_OPT_TAIL_SMEM_KB 24 /* shared memory a tail-pipeline CTA asks for (default 224 KB = the whole SM: keeps every other CTA off its schedulers) */
 #define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */
 #define B200_OPT_STREAM_LAG1 15  /* ... frame slots between pass 1 and pass 2 of a frame in the item order (default 2) */
 #define B200_OPT_STREAM_LAG2 16  /* ... between pass 1 and the quantiser (default 4) */
@@ -42,9 +43,10 @@ extern "C" {
 /* Sets a tuning knob (the B200_OPT_* values above) or an engine option. 0 or a negative B200_E* code. */
 int b200_debug_option(b200_engine *e, int knob, int value);
 
-/* Profiling aid: accumulate the SM-clock cycles block 0 of the client tail kernel spends in each of its
- * seven phases (load, sum1, avg, sum2, peak, gain, store). out (nullable) receives the totals so far. */
-int b200_debug_tail_profile(b200_engine *e, int enable, long long out[32]);
+/* Profiling aid: accumulate, per stage warp of group 0 of the client tail pipeline (stage ids: 0 load, 1 sum1, 2 sum2,
+ * 3 block, 4 gain, 5..8 peak, 9..12 out, 13..14 suffix), the SM-clock cycles spent waiting for input, waiting for ring
+ * space, and in total: out[3 * stage + {0, 1, 2}]. out (nullable) receives the totals so far. */
+int b200_debug_tail_profile(b200_engine *e, int enable, long long out[64]);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,9 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kT2Warps = 10;
+constexpr int kT2NPeak = 4, kT2NOut = 4, kT2NSuf = 2;   // warps of the stages that have no loop-carried state: chunks
+                                                         // (suffix: frames) are dealt round-robin
+constexpr int kT2Warps = 16;
 constexpr int kT2Threads = 32 * kT2Warps;
 constexpr int kT2CH = 32;      // samples per chunk
 constexpr int kT2Depth = 4;    // chunks a producer may run ahead of its consumer
@@ -70,7 +72,25 @@ __host__ __device__ inline size_t tail2_smem(int D) {
     const size_t nsx = (size_t)D + (kT2Depth + 1) * kT2CH;
     const size_t chunk = sizeof(float) * kT2CH * kT2Pitch;
     //     X, M rings                                Y R D G rings          out (2 x 2), peak (2 x 2), suffix (2) staging   barriers
-    return 2 * sizeof(float) * nsx * kT2Pitch + 4 * kT2Depth * chunk + 10 * chunk + 1024;
+    return 2 * sizeof(float) * nsx * kT2Pitch + 4 * kT2Depth * chunk + 2 * (kT2NOut + kT2NPeak + kT2NSuf) * chunk + 1024;
+}
+
+// slow path of a bounded mbarrier wait, out of line: the stages' hot loops stay small (ten warps run ten different loops,
+// and the instruction caches are what they compete for)
+__device__ __noinline__ bool t2_wait_slow(uint64_t *bar, unsigned parity, int *s_abort, int *err, int code) {
+    unsigned long long t0 = 0;
+    for (unsigned spins = 1;; spins++) {
+        if (mbar_try_wait(bar, parity)) return true;
+        if ((spins & 63u) == 0) {
+            if (*reinterpret_cast<volatile int *>(s_abort)) return false;
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) {
+                if (atomicCAS(s_abort, 0, 1) == 0) atomicCAS(err, 0, code);  // first stage to give up
+                return false;
+            }
+        }
+    }
 }
 
 template <int G>
@@ -90,9 +110,9 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
     float *rG = rD + NR * P;               // gain
     float *stgO = rG + NR * P;             // out stage: [2 warps][2 buffers][CH][P] delayed samples (front of the look-ahead
                                            // buffer) copied straight from the look-ahead ring, turned into int16 results in place
-    float *stgP = stgO + 4 * CH * P;       // peak stage: [2 warps][2 buffers][CH][P] suffix-maximum rows of the look-ahead ring
-    float *stgS = stgP + 4 * CH * P;       // suffix stage: [2 buffers][CH][P]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(stgS + 2 * CH * P);
+    float *stgP = stgO + 2 * kT2NOut * CH * P;   // peak stage: [warps][2 buffers][CH][P] suffix-maximum rows of the look-ahead ring
+    float *stgS = stgP + 2 * kT2NPeak * CH * P;  // suffix stage: [warps][2 buffers][CH][P]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(stgS + 2 * kT2NSuf * CH * P);
     // edges: 0 X (load -> sum1, sum2)  1 M (sum1 -> sum2)  2 Y (sum2 -> block)  3 R (block -> peak)  4 D (peak -> gain)
     //        5 (unused)  6 G (gain -> out)  7 B (block -> suffix, one slot per FRAME)
     constexpr int BS = 4;  // barrier slots reserved per edge and direction
@@ -103,7 +123,17 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
     int &s_abort = s_abort_all[sub];
     unsigned char(*s_valid)[32] = s_valid_all[sub];
 
-    const int tid = (int)threadIdx.x - sub * kT2Threads, warp = tid >> 5, lane = tid & 31;
+    // Stage of this warp. Warp w issues from scheduler w % 4: each scheduler gets ONE of the four stages with a loop-carried
+    // recurrence (sum1, sum2, gain, block - the critical path) plus warps that run the same code as one another, so that
+    // the 6 KB L0 instruction cache of a scheduler holds three loops, not four or five.
+    enum { R_LOAD = 0, R_SUM1 = 1, R_SUM2 = 2, R_BLOCK = 3, R_GAIN = 4, R_PEAK = 5, R_OUT = R_PEAK + kT2NPeak, R_SUF = R_OUT + kT2NOut,
+           R_IDLE = R_SUF + kT2NSuf };
+    static_assert(R_IDLE <= kT2Warps && kT2NPeak == 4 && kT2NOut == 4 && kT2NSuf == 2, "role table below");
+    const int tid = (int)threadIdx.x - sub * kT2Threads, hw_warp = tid >> 5, lane = tid & 31;
+    //                                   scheduler 0..3 | 0..3                        | 0..3                            | 0..3
+    constexpr int kRole[kT2Warps] = {R_SUM1, R_SUM2, R_GAIN, R_BLOCK, R_PEAK, R_PEAK + 2, R_OUT, R_OUT + 2,
+                                     R_PEAK + 1, R_PEAK + 3, R_OUT + 1, R_OUT + 3, R_LOAD, R_SUF, R_SUF + 1, R_IDLE};
+    const int warp = kRole[hw_warp];
     const int grp = (int)blockIdx.x * G + sub;
     const int slot = grp * 32 + lane;
     const bool in_range = slot < ca.max_clients;
@@ -130,21 +160,8 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
 
     // bounded waits: a stage that never gets its chunk is a bug in this file - flag it and leave instead of hanging
     auto wait_bar = [&](uint64_t *bar, unsigned parity) -> bool {
-        const int bar_id = (int)(bar - bars);  // (edge, full/empty, slot) - reported when the wait expires
         if (mbar_try_wait(bar, parity)) return true;
-        unsigned long long t0 = 0;
-        for (unsigned spins = 1;; spins++) {
-            if (mbar_try_wait(bar, parity)) return true;
-            if ((spins & 63u) == 0) {
-                if (*reinterpret_cast<volatile int *>(&s_abort)) return false;
-                const unsigned long long now = global_ns();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > 2000000000ull) {
-                    if (atomicCAS(&s_abort, 0, 1) == 0) atomicCAS(st.err, 0, 10000 + warp * 100 + bar_id);  // first stage to give up
-                    return false;
-                }
-            }
-        }
+        return t2_wait_slow(bar, parity, &s_abort, st.err, 10000 + warp * 100 + (int)(bar - bars));  // (stage, edge / direction / slot)
     };
     // profiling aid (cl.prof != nullptr): cycles the warps of CTA 0 spend waiting for input / for ring space, and in total
     const bool prof = cl.prof != nullptr && grp == 0 && lane == 0;
@@ -213,13 +230,33 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
         }
     };
 
+    // the same walk for the stages whose warps take every N-th chunk: chunk number, frame, chunk in frame, and the two
+    // per-frame counters that advance with every frame the NaN guard let through
+    struct Walk {
+        int q, f, ci, blk, since;  // blk: look-ahead block that frame f fills; since: samples pushed before frame f (saturates at L)
+    };
+    auto walk_first = [&](int blk0, int since0) { return Walk{0, 0, 0, blk0, since0}; };
+    auto walk = [&](Walk &w, int n) {  // n chunks on (the caller keeps w.q + n < nq)
+        for (int i = 0; i < n; i++) {
+            w.q++;
+            if (++w.ci == cpf) {
+                w.ci = 0;
+                if (valid_of(w.f)) {
+                    if (++w.blk == NB) w.blk = 0;
+                    w.since = min(w.since + h, L);
+                }
+                w.f++;
+            }
+        }
+    };
+
     // Code size and instruction count matter here: every stage is ONE instruction stream, so its time is its instruction
     // count times the issue latency of dependent instructions. Loops stay rolled (register batches of eight samples,
     // addressed by one pointer plus compile-time offsets; the rare batch that straddles the end of a ring or the end of a
     // chunk takes a generic path), and global memory is read with asynchronous copies.
     // ring element (idx, lane) of a [samples][P] ring
 #define T2_AT(ring, idx) ((ring) + (idx) * P + lane)
-    if (warp == 0) {
+    if (warp == R_LOAD) {
         // ================= load: audio rows -> X ring (transposed), DC input history =================
         // history: ring positions nsx - D .. nsx - 1 precede position 0 of the common timeline
         for (int i = 0; i < D; i++) {
@@ -230,16 +267,18 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
         // one client row at a time, lanes along the samples of the chunk (coalesced), copied straight to their transposed
         // place; up to DEPTH - 1 chunks are requested ahead of the one being handed over
         int pos_issue = 0, q_issue = 0;
+        const int nrows = min(32, ca.max_clients - grp * 32);
         ChunkIt ci = chunk_first();
         auto issue = [&]() -> bool {
             if (!wait_bar(empty(0) + ci.slot, ci.par ^ 1)) return false;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid_of(ci.f));
+            // (rows of dropped frames and of inactive slots are copied too: nothing reads them - a dropped frame's lane only
+            // ever looks at the last D positions, which the replay below rewrites - and one unpredicated copy per row with
+            // two pointer bumps is a fifth of the instructions of the selective loop)
             const float *src = ca.audio_pre + ((size_t)ci.f * ca.max_clients + grp * 32) * h + ci.a + lane;
             float *dst = rX + wrapx(pos_issue + lane) * P;
             if (lane < ci.len) {
 #pragma unroll 8
-                for (int c = 0; c < 32; c++)
-                    if ((vmask >> c) & 1u) cp_async4(dst + c, src + (size_t)c * h);
+                for (int c = 0; c < nrows; c++, src += h, dst++) cp_async4(dst, src);
             }
             cp_async_commit();
             pos_issue = wrapx(pos_issue + ci.len);
@@ -273,7 +312,7 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
         __syncwarp();
         if (active)
             for (int i = 0; i < D; i++) st.dcx[((size_t)grp * D + i) * 32 + lane] = rX[wrapx(pos + nsx - D + i) * P + lane];
-    } else if (warp == 1) {
+    } else if (warp == R_SUM1) {
         // ================= sum1: first running sum of the DC blocker, src/utils.h:80-85 =================
         float s1 = (active && !reset_all) ? st.sum[((size_t)grp * 2 + 0) * 32 + lane] : 0.f;
         for (int i = 0; i < D; i++) {
@@ -329,7 +368,7 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
             st.sum[((size_t)grp * 2 + 0) * 32 + lane] = s1;
             for (int i = 0; i < D; i++) st.dcm[((size_t)grp * D + i) * 32 + lane] = rM[wrapx(pos + nsx - D + i) * P + lane];
         }
-    } else if (warp == 2) {
+    } else if (warp == R_SUM2) {
         // ================= sum2: second running sum; y = x[delayed] - ma2, src/utils.h:145-149 =================
         float s2 = (active && !reset_all) ? st.sum[((size_t)grp * 2 + 1) * 32 + lane] : 0.f;
         int pos = 0;
@@ -374,7 +413,7 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
             pos = wrapx(pos + len);
         }
         if (active) st.sum[((size_t)grp * 2 + 1) * 32 + lane] = s2;
-    } else if (warp == 3) {
+    } else if (warp == R_BLOCK) {
         // ================= block: running maximum, look-ahead ring, block maximum =================
         int blk = active ? st.blk[g32] : 0;
         float *ring = st.ring + (size_t)grp * NB * h * 32 + lane;
@@ -425,28 +464,23 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
             }
         }
         if (active) st.blk[g32] = blk;
-    } else if (warp == 4 || warp == 5) {
-        // ================= peak: delayed sample, window maximum, desired gain (audioprocessing.cpp:41-52) =================
-        const int me = warp - 4;
-        int blk = active ? st.blk[g32] : 0;   // block that the frame being processed fills
-        int blk_i = blk;                      // ... that the frame whose rows are being requested fills
+    } else if (warp >= R_PEAK && warp < R_PEAK + kT2NPeak) {
+        // ================= peak: window maximum -> desired gain (audioprocessing.cpp:41-52); chunks q = me (mod NP) ========
+        constexpr int NP = kT2NPeak;
+        const int me = warp - R_PEAK;
         const float *suf = st.suf + (size_t)grp * NB * h * 32 + lane;
         const float *cmx = st.cmax + (size_t)grp * NB * 32 + lane;
         const int kb = st.kb, col0 = st.col0;
         float *stg = stgP + me * 2 * CH * P + lane;   // [buffer][CH][P]
-        const int nown = (cpf - me + 1) / 2;          // own chunks per frame: ci = me, me + 2, ...
-        const int total = F * nown;
-        // rows of the look-ahead ring (delayed samples and their suffix maxima) for own chunk number k: they were written at
-        // least kb - 1 frames ago, so they are requested one own chunk ahead, independent of the frame being pushed
-        int fi = 0, cii = me;   // frame / chunk-in-frame of the own chunk whose rows are requested next
-        auto issue = [&](int k) {
-            const int f = fi, ci = cii, a = ci * CH, len = min(CH, h - a);
-            if (k > 0 && ci == me && valid_of(f - 1) && ++blk_i == NB) blk_i = 0;  // first own chunk of a new frame
-            if (valid_of(f)) {
-                int c0 = blk_i - kb;
+        // rows of the suffix maxima for chunk w: they were written at least kb - 1 frames ago, so they are requested one own
+        // chunk ahead, independent of the frame being pushed
+        auto request = [&](const Walk &w, int buf) {
+            if (valid_of(w.f)) {
+                const int a = w.ci * CH, len = min(CH, h - a);
+                int c0 = w.blk - kb;
                 if (c0 < 0) c0 += NB;
                 const int c1 = (c0 + 1 == NB) ? 0 : c0 + 1;
-                float *d = stg + (k & 1) * CH * P;
+                float *d = stg + buf * CH * P;
                 // the chunk's window ends walk through block c0 from column col0 + a, then through block c1 from column 0
                 const int i0 = col0 + a, n0 = max(0, min(len, h - i0));
                 const float *g0 = suf + ((size_t)c0 * h + i0) * 32, *g1 = suf + ((size_t)c1 * h + (i0 + n0 - h)) * 32;
@@ -456,72 +490,69 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
                 for (int j = n0; j < len; j++) cp_async4(d + j * P, g1 + (size_t)(j - n0) * 32);
             }
             cp_async_commit();
-            cii += 2;
-            if (cii >= cpf) {
-                cii = me;
-                fi++;
-            }
         };
-        if (total > 0) issue(0);
-        float m0 = 0.f, m1 = 0.f;  // maxima of the whole blocks strictly between the walking block and this frame
-        int f = 0, ci = me;
-        for (int k = 0; k < total; k++) {
-            const int a = ci * CH, len = min(CH, h - a);
-            const int q = f * cpf + ci;
-            const bool v = valid_of(f);
-            if (k + 1 < total) {
-                issue(k + 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            T2_WAIT_FULL(3, q);  // (also orders this after the previous frame's block maximum)
-            if (ci == me) {      // first own chunk of the frame: the block maxima in between
-                m0 = m1 = 0.f;
-                if (v) {
-                    int c = blk - kb + 1;
-                    if (c < 0) c += NB;
-                    for (int i = 1; i < kb; i++) {
-                        const float x = cmx[(size_t)c * 32];
-                        m0 = fmaxf(m0, x);
-                        if (i >= 2) m1 = fmaxf(m1, x);
-                        if (++c == NB) c = 0;
-                    }
+        if (me < nq) {
+            Walk cur = walk_first(active ? st.blk[g32] : 0, 0), nxt = cur;
+            walk(cur, me);
+            request(cur, 0);
+            float m0 = 0.f, m1 = 0.f;  // maxima of the whole blocks strictly between the walking block and this frame
+            int f_m = -1;
+            for (int k = 0;; k++) {
+                const bool more = cur.q + NP < nq;
+                if (more) {
+                    nxt = cur;
+                    walk(nxt, NP);
+                    request(nxt, (k + 1) & 1);
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
                 }
-            }
-            T2_WAIT_EMPTY(4, q);
-            if (v) {
-                const float *d = stg + (k & 1) * CH * P;
-                const float *rp = T2_AT(rR, (q % DEPTH) * CH);
-                float *dp = T2_AT(rD, (q % DEPTH) * CH);
-                const int nfirst = max(0, min(len, h - (col0 + a)));  // samples whose window end is still in block c0
-                for (int j0 = 0; j0 < len; j0 += U, d += U * P, rp += U * P, dp += U * P) {
-                    if (j0 + U <= len && (j0 + U <= nfirst || j0 >= nfirst)) {
-                        const float mid = (j0 < nfirst) ? m0 : m1;
-                        float pk[U];
-#pragma unroll
-                        for (int u = 0; u < U; u++) pk[u] = __fadd_rn(fmaxf(fmaxf(d[u * P], mid), rp[u * P]), 1e-10f);
-#pragma unroll
-                        for (int u = 0; u < U; u++) dp[u * P] = __fdiv_rn(ca.desired, pk[u]);
-                    } else {
-                        for (int u = 0; u < U && j0 + u < len; u++) {
-                            const float mid = (j0 + u < nfirst) ? m0 : m1;
-                            dp[u * P] = __fdiv_rn(ca.desired, __fadd_rn(fmaxf(fmaxf(d[u * P], mid), rp[u * P]), 1e-10f));
+                const int q = cur.q, f = cur.f, a = cur.ci * CH, len = min(CH, h - a);
+                const bool v = valid_of(f);
+                T2_WAIT_FULL(3, q);  // (also orders this after the previous frame's block maximum)
+                if (f != f_m) {      // first own chunk of the frame: the block maxima in between
+                    f_m = f;
+                    m0 = m1 = 0.f;
+                    if (v) {
+                        int c = cur.blk - kb + 1;
+                        if (c < 0) c += NB;
+                        for (int i = 1; i < kb; i++) {
+                            const float x = cmx[(size_t)c * 32];
+                            m0 = fmaxf(m0, x);
+                            if (i >= 2) m1 = fmaxf(m1, x);
+                            if (++c == NB) c = 0;
                         }
                     }
                 }
-            }
-            T2_SIGNAL(full(4), q);
-            T2_SIGNAL(empty(3), q);
-            if (ci + 2 >= cpf) {  // last own chunk of the frame
-                if (v && ++blk == NB) blk = 0;
-                ci = me;
-                f++;
-            } else {
-                ci += 2;
+                T2_WAIT_EMPTY(4, q);
+                if (v) {
+                    const float *d = stg + (k & 1) * CH * P;
+                    const float *rp = T2_AT(rR, (q % DEPTH) * CH);
+                    float *dp = T2_AT(rD, (q % DEPTH) * CH);
+                    const int nfirst = max(0, min(len, h - (col0 + a)));  // samples whose window end is still in block c0
+                    for (int j0 = 0; j0 < len; j0 += U, d += U * P, rp += U * P, dp += U * P) {
+                        if (j0 + U <= len && (j0 + U <= nfirst || j0 >= nfirst)) {
+                            const float mid = (j0 < nfirst) ? m0 : m1;
+                            float pk[U];
+#pragma unroll
+                            for (int u = 0; u < U; u++) pk[u] = __fadd_rn(fmaxf(fmaxf(d[u * P], mid), rp[u * P]), 1e-10f);
+#pragma unroll
+                            for (int u = 0; u < U; u++) dp[u * P] = __fdiv_rn(ca.desired, pk[u]);
+                        } else {
+                            for (int u = 0; u < U && j0 + u < len; u++) {
+                                const float mid = (j0 + u < nfirst) ? m0 : m1;
+                                dp[u * P] = __fdiv_rn(ca.desired, __fadd_rn(fmaxf(fmaxf(d[u * P], mid), rp[u * P]), 1e-10f));
+                            }
+                        }
+                    }
+                }
+                T2_SIGNAL(full(4), q);
+                T2_SIGNAL(empty(3), q);
+                if (!more) break;
+                cur = nxt;
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == R_GAIN) {
         // ================= gain: attack / release recurrence, audioprocessing.cpp:54-63 =================
         float gain = (active && !reset_agc) ? st.gain[g32] : 0.f;
         int since = (active && !reset_agc) ? st.since[g32] : 0;
@@ -568,62 +599,58 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
             st.gain[g32] = gain;
             st.since[g32] = since;
         }
-    } else if (warp == 7 || warp == 8) {
+    } else if (warp >= R_OUT && warp < R_OUT + kT2NOut) {
         // ================= out: delayed sample * gain -> int16 (dsp.cpp:152-165 with mult = 65536 / 4), transposed store ====
-        // (two warps, alternate chunks)
-        const int me = warp - 7;
-        int since = (active && !reset_agc) ? st.since[g32] : 0;
+        // chunks q = me (mod NO)
+        constexpr int NO = kT2NOut;
+        const int me = warp - R_OUT;
         const unsigned amask = __ballot_sync(0xffffffffu, active);
         const float *ring = st.ring + (size_t)grp * NB * h * 32 + lane;
         const int kb = st.kb, col0 = st.col0;
         float *stg = stgO + me * 2 * CH * P;   // [buffer][CH][P]
+        if (me == 0 && active)
+            for (int f = 0; f < F; f++) ca.valid[(size_t)f * ca.max_clients + slot] = valid_of(f) ? 1 : 0;
         // The delayed samples of a chunk are rows of the look-ahead ring written at least kb - 1 frames ago: they are
         // requested one own chunk ahead, independent of every other stage.
-        auto advance = [&](ChunkIt &x, int &b) {  // next chunk; b = look-ahead block that x's frame fills
-            const int f0 = x.f;
-            chunk_next(x);
-            if (x.f != f0 && valid_of(f0) && ++b == NB) b = 0;
-        };
-        auto request = [&](const ChunkIt &x, int b, int buf) {
-            if (valid_of(x.f)) {
-                int c0 = b - kb;
+        auto request = [&](const Walk &w, int buf) {
+            if (valid_of(w.f)) {
+                const int a = w.ci * CH, len = min(CH, h - a);
+                int c0 = w.blk - kb;
                 if (c0 < 0) c0 += NB;
                 const int c1 = (c0 + 1 == NB) ? 0 : c0 + 1;
                 float *d = stg + buf * CH * P + lane;
-                const int i0 = col0 + x.a, n0 = max(0, min(x.len, h - i0));
+                const int i0 = col0 + a, n0 = max(0, min(len, h - i0));
                 const float *g0 = ring + ((size_t)c0 * h + i0) * 32, *g1 = ring + ((size_t)c1 * h + (i0 + n0 - h)) * 32;
 #pragma unroll 8
                 for (int j = 0; j < n0; j++) cp_async4(d + j * P, g0 + (size_t)j * 32);
 #pragma unroll 8
-                for (int j = n0; j < x.len; j++) cp_async4(d + j * P, g1 + (size_t)(j - n0) * 32);
+                for (int j = n0; j < len; j++) cp_async4(d + j * P, g1 + (size_t)(j - n0) * 32);
             }
             cp_async_commit();
         };
-        int blk = active ? st.blk[g32] : 0;
-        ChunkIt c = chunk_first();
-        ChunkIt cn = c;   // the own chunk whose rows are requested next
-        int blk_n = blk, qn = 0, k = 0;
-        for (; qn < me && qn < nq - 1; qn++) advance(cn, blk_n);
-        if (me < nq) request(cn, blk_n, 0);
-        for (int q = 0; q < nq; q++) {
-            const int f = c.f, a = c.a, len = c.len;
-            const bool v = valid_of(f);
-            if ((q & 1) == me) {
-                if (q + 2 < nq) {
-                    advance(cn, blk_n);
-                    advance(cn, blk_n);
-                    request(cn, blk_n, (k + 1) & 1);
+        if (me < nq) {
+            Walk cur = walk_first(active ? st.blk[g32] : 0, (active && !reset_agc) ? st.since[g32] : 0), nxt = cur;
+            walk(cur, me);
+            request(cur, 0);
+            for (int k = 0;; k++) {
+                const bool more = cur.q + NO < nq;
+                if (more) {
+                    nxt = cur;
+                    walk(nxt, NO);
+                    request(nxt, (k + 1) & 1);
                     cp_async_wait<1>();
                 } else {
                     cp_async_wait<0>();
                 }
-                T2_WAITC_FULL(6, c);
+                const int q = cur.q, f = cur.f, a = cur.ci * CH, len = min(CH, h - a);
+                const bool v = valid_of(f);
+                T2_WAIT_FULL(6, q);
                 int *tile = reinterpret_cast<int *>(stg + (k & 1) * CH * P);  // results replace the delayed samples in place
-                k++;
                 const float *op = reinterpret_cast<const float *>(tile) + lane;
-                const float *gp = T2_AT(rG, c.slot * CH);
+                const float *gp = T2_AT(rG, (q % DEPTH) * CH);
                 int *tp = tile + lane;
-                const int first = v ? max(0, min(len, L - 1 - since - a)) : len;
+                // outputs stay 0 until the look-ahead buffer is full (audioprocessing.cpp:45,64-66)
+                const int first = v ? max(0, min(len, L - 1 - cur.since - a)) : len;
                 for (int j0 = 0; j0 < len; j0 += U, op += U * P, gp += U * P, tp += U * P) {
                     if (v && first == 0 && j0 + U <= len) {
                         float o[U], gg[U];
@@ -648,81 +675,94 @@ __global__ void __launch_bounds__(kT2Threads *G) client_tail2_kernel(const Clien
                         }
                     }
                 }
-                T2_SIGNALC(empty(6), c);
+                T2_SIGNAL(empty(6), q);
                 __syncwarp();
                 // one client row at a time, lanes along the samples of the chunk
                 if (!st.pcm16) {
                     int *prow = ca.pcm + ((size_t)f * ca.max_clients + grp * 32) * h + a + lane;
                     const int *tr = tile + lane * P;
                     if (lane < len) {
+                        if (amask == 0xffffffffu) {  // (the usual case: no predicate, two pointer bumps per row)
 #pragma unroll 8
-                        for (int c = 0; c < 32; c++)
-                            if ((amask >> c) & 1u) prow[(size_t)c * h] = tr[c];
+                            for (int c = 0; c < 32; c++, prow += h, tr++) *prow = *tr;
+                        } else {
+#pragma unroll 8
+                            for (int c = 0; c < 32; c++)
+                                if ((amask >> c) & 1u) prow[(size_t)c * h] = tr[c];
+                        }
                     }
                 } else {
                     // int16 rows: h int16 = h / 2 words (a is a multiple of 32 and h is even, so every row offset is even)
                     unsigned *p16 =
                         reinterpret_cast<unsigned *>(ca.pcm) + ((((size_t)f * ca.max_clients + grp * 32) * h + a) >> 1) + lane;
                     if (2 * lane < len) {
+                        const int *t0 = tile + (2 * lane) * P, *t1 = t0 + ((2 * lane + 1 < len) ? P : 0);
+                        const unsigned keep_hi = (2 * lane + 1 < len) ? 0xFFFFFFFFu : 0u;
+                        const int hw = h >> 1;
+                        if (amask == 0xffffffffu) {
 #pragma unroll 8
-                        for (int c = 0; c < 32; c++) {
-                            if (!((amask >> c) & 1u)) continue;
-                            const int lo = tile[(2 * lane) * P + c];
-                            const int hi = (2 * lane + 1 < len) ? tile[(2 * lane + 1) * P + c] : 0;
-                            p16[((size_t)c * h) >> 1] = ((unsigned)lo & 0xFFFFu) | ((unsigned)hi << 16);
+                            for (int c = 0; c < 32; c++, p16 += hw, t0++, t1++)
+                                *p16 = ((unsigned)*t0 & 0xFFFFu) | (((unsigned)*t1 << 16) & (keep_hi & 0xFFFF0000u));
+                        } else {
+#pragma unroll 8
+                            for (int c = 0; c < 32; c++) {
+                                if (!((amask >> c) & 1u)) continue;
+                                p16[(size_t)c * hw] = ((unsigned)t0[c] & 0xFFFFu) | (((unsigned)t1[c] << 16) & (keep_hi & 0xFFFF0000u));
+                            }
                         }
                     }
                 }
                 __syncwarp();
+                if (!more) break;
+                cur = nxt;
             }
-            if (a + len == h) {
-                if (active && ((f & 1) == me)) ca.valid[(size_t)f * ca.max_clients + slot] = v ? 1 : 0;
-                if (v) since = min(since + h, L);
-            }
-            if (q + 1 < nq) chunk_next(c);
         }
-    } else {
-        // ================= suffix: in-block suffix maxima of |y| for every finished block =================
+    } else if (warp >= R_SUF && warp < R_SUF + kT2NSuf) {
+        // ================= suffix: in-block suffix maxima of |y| for every finished block; frames f = me (mod NS) =========
+        constexpr int NS = kT2NSuf;
+        const int me = warp - R_SUF;
         int blk = active ? st.blk[g32] : 0;
         const float *ring = st.ring + (size_t)grp * NB * h * 32 + lane;
         float *suf = st.suf + (size_t)grp * NB * h * 32 + lane;
-        float *stg = stgS + lane;   // [buffer][CH][P]
+        float *stg = stgS + me * 2 * CH * P + lane;   // [buffer][CH][P]
         for (int f = 0; f < F; f++) {
             const bool v = valid_of(f);
-            T2_WAIT_FULL(7, f);
-            if (v) {
-                const float *rowp = ring + (size_t)blk * h * 32;
-                float *sp = suf + (size_t)blk * h * 32;
-                // backwards in batches of CH rows; batch b + 1 is requested while batch b is scanned
-                auto issue = [&](int b) {
-                    const int j1 = h - b * CH, j0 = max(0, j1 - CH);
-                    float *d = stg + (b & 1) * CH * P;
-                    const float *g = rowp + (size_t)j0 * 32;
+            if (f % NS == me) {
+                T2_WAIT_FULL(7, f);
+                if (v) {
+                    const float *rowp = ring + (size_t)blk * h * 32;
+                    float *sp = suf + (size_t)blk * h * 32;
+                    // backwards in batches of CH rows; batch b + 1 is requested while batch b is scanned
+                    auto issue = [&](int b) {
+                        const int j1 = h - b * CH, j0 = max(0, j1 - CH);
+                        float *d = stg + (b & 1) * CH * P;
+                        const float *g = rowp + (size_t)j0 * 32;
 #pragma unroll 4
-                    for (int j = 0; j < j1 - j0; j++) cp_async4(d + j * P, g + (size_t)j * 32);
-                    cp_async_commit();
-                };
-                issue(0);
-                float sm = 0.f;
-                for (int b = 0; b < cpf; b++) {
-                    const int j1 = h - b * CH, j0 = max(0, j1 - CH);
-                    if (b + 1 < cpf) {
-                        issue(b + 1);
-                        cp_async_wait<1>();
-                    } else {
-                        cp_async_wait<0>();
-                    }
-                    const float *d = stg + (b & 1) * CH * P;
-                    float *so = sp + (size_t)j0 * 32;
+                        for (int j = 0; j < j1 - j0; j++) cp_async4(d + j * P, g + (size_t)j * 32);
+                        cp_async_commit();
+                    };
+                    issue(0);
+                    float sm = 0.f;
+                    for (int b = 0; b < cpf; b++) {
+                        const int j1 = h - b * CH, j0 = max(0, j1 - CH);
+                        if (b + 1 < cpf) {
+                            issue(b + 1);
+                            cp_async_wait<1>();
+                        } else {
+                            cp_async_wait<0>();
+                        }
+                        const float *d = stg + (b & 1) * CH * P;
+                        float *so = sp + (size_t)j0 * 32;
 #pragma unroll 4
-                    for (int j = j1 - j0 - 1; j >= 0; j--) {
-                        sm = fmaxf(sm, fabsf(d[j * P]));
-                        so[(size_t)j * 32] = sm;
+                        for (int j = j1 - j0 - 1; j >= 0; j--) {
+                            sm = fmaxf(sm, fabsf(d[j * P]));
+                            so[(size_t)j * 32] = sm;
+                        }
                     }
                 }
-                if (++blk == NB) blk = 0;
+                T2_SIGNAL(empty(7), f);
             }
-            T2_SIGNAL(empty(7), f);
+            if (v && ++blk == NB) blk = 0;
         }
     }
 #undef T2_AT

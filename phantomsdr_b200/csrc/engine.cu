@@ -253,6 +253,8 @@ struct b200_engine {
     int opt_client_mask = 3;            // profiling aid: bit0 = demodulation kernels, bit1 = tail kernel
     int opt_demod_chunk = 8;            // frames per warp task of the frame-chunked demodulation (0 = sequential kernel only)
     int flag_waits = 0;                 // b200_enqueue_wait calls since stream_check last read the flag error word
+    int opt_tail_smem_kb = 224;         // shared memory a tail CTA asks for: with its 3 KB of static memory exactly the SM's 227 KB,
+                                        // so that no other CTA (not even a pyramid CTA with 1 KB) shares its schedulers
     int opt_demod_generic = 0;          // 1: never use the compile-time-size demodulation kernel (comparison aid)
     int demod_wpc = 0;                  // warps per CTA of client_demod_warp_kernel (0 = audio FFT too long: sequential kernel)
     int cstate = 0;                     // which copy of the overlap state the next client batch reads
@@ -1123,11 +1125,12 @@ template <int KB> int launch_tail_kb(b200_engine *e, const ClientArrays &ca, con
     return 0;
 }
 int launch_tail2(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
-    // One group of 32 clients per CTA, and the CTA asks for (nearly) all the shared memory of its SM although it needs
-    // about half: every stage of the pipeline is a single warp on the critical path, and warps of other CTAs competing
-    // for the SM's issue slots slow the whole chain. Measured at 1024 clients beside the forward kernels: two groups
-    // per SM (as two CTAs or as one CTA of 20 warps) 16.9 us/frame of tails and 23-26 GS/s, one group per SM 11.3 and 31.
-    const size_t smem = std::max(tail2_smem(e->ca.D), (size_t)200 * 1024);
+    // One group of 32 clients per CTA, and the CTA asks for ALL the shared memory of its SM although it needs 204 KB:
+    // every stage of the pipeline is a single warp on the critical path, and warps of other CTAs competing for the SM's
+    // issue slots slow the whole chain. Measured at 1024 clients beside the forward kernels (cycles per frame of a
+    // stage-profiled CTA): alone 16.4 K; beside the forward kernels 22.3 K at 204 KB (pyramid CTAs move in), 19.3 K at
+    // 224 KB. Two groups per SM (two CTAs, or one CTA of twice the warps) cost every stage 40 %.
+    const size_t smem = std::max(tail2_smem(e->ca.D), (size_t)e->opt_tail_smem_kb * 1024);
     if (cl.nactive == 0) {  // preparation call from clients_create
         CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return 0;
@@ -1493,6 +1496,13 @@ int b200_debug_option(b200_engine *e, int option, int value) {
         e->opt_sub_frames = value;
         return 0;
     case B200_OPT_DEMOD_GENERIC: e->opt_demod_generic = value ? 1 : 0; return 0;
+    case B200_OPT_TAIL_SMEM_KB:
+        if (value < 0 || value > 224) return fail(B200_EINVAL, "tail shared memory must be 0..224 KB");
+        e->opt_tail_smem_kb = value;
+        if (e->have_clients && e->use_tail2)
+            CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)std::max(tail2_smem(e->ca.D), (size_t)value * 1024)));
+        return 0;
     case B200_OPT_FWD_SMS:
         if (value < 0 || value > 1024) return fail(B200_EINVAL, "forward SM count must be 0 (all) .. 1024");
         e->opt_fwd_sms = value;
@@ -2282,17 +2292,17 @@ int b200_quant_table(int power_offset, uint32_t *lo, uint32_t *hi, uint8_t *base
     return 0;
 }
 
-int b200_debug_tail_profile(b200_engine *e, int enable, long long out[32]) {
+int b200_debug_tail_profile(b200_engine *e, int enable, long long out[64]) {
     if (!e) return fail(B200_EINVAL, "null engine");
     CU(cudaSetDevice(e->device));
     if (e->d_prof && out) {
         CU(cudaDeviceSynchronize());
-        CU(cudaMemcpy(out, e->d_prof, sizeof(long long) * 32, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(out, e->d_prof, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
     }
     if (enable && !e->d_prof) {
-        CU(cudaMalloc(&e->d_prof, sizeof(long long) * 32));
+        CU(cudaMalloc(&e->d_prof, sizeof(long long) * 64));
     }
-    if (e->d_prof) CU(cudaMemset(e->d_prof, 0, sizeof(long long) * 32));
+    if (e->d_prof) CU(cudaMemset(e->d_prof, 0, sizeof(long long) * 64));
     if (!enable && e->d_prof) {
         cudaFree(e->d_prof);
         e->d_prof = nullptr;
