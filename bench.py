@@ -751,8 +751,9 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
                              pwr=eng.pinned(4 * F * args.clients, np.float32),
                              valid=eng.pinned(F * args.clients, np.uint8),
                              pyr=eng.pinned(F * eng.pyramid_bytes, np.int8)))
-        n_send = len(range(0, F, wf_skip)) if F % wf_skip == 0 else None  # send frames per block (exact when skip | F)
-        dbytes_frame = (eng.pyramid_bytes / wf_skip if n_send else eng.pyramid_bytes) + args.clients * (h * pcm_bytes + 5)
+        # pyramids come back only for the send frames (frame_num % skip == 0) of the timed frames 3F .. 3F + nblk F
+        n_send = sum(1 for f in range(3 * F, 3 * F + nblk * F) if f % wf_skip == 0)
+        dbytes_frame = eng.pyramid_bytes * n_send / (nblk * F) + args.clients * (h * pcm_bytes + 5)
 
         def host_halves(dt):
             halves_sets = []

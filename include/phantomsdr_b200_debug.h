@@ -32,7 +32,7 @@ extern "C" {
 #define B200_OPT_CLIENT_STAGE_MASK 20 /* profiling aid: bit0 = demodulation kernels, bit1 = tail kernel; default 3 */
 #define B200_OPT_FWD_SMS 21      /* SMs the persistent pass-2 kernel sizes its grid for (0 = all): with the tail kernel resident on
                                   * some SMs a one-CTA-per-SM grid would run in two waves */
-#define B200_OPT_PASS1_SPLIT 22  /* CTAs per column tile of the TMA pass 1 (default 2); more = finer work units for the block scheduler */
+#define B200_OPT_PASS1_SPLIT 22  /* CTAs per column tile of the TMA pass 1 (default 16 = work units of four frames at 64 frames per launch) */
 #define B200_OPT_DEMOD_GENERIC 23 /* comparison aid: 1 = run-time-plan demodulation kernel even for audio_fft_size 360 */
 #define B200_OPT_TAIL_SMEM_KB 24 /* shared memory a tail-pipeline CTA asks for (default 224 KB = the whole SM: keeps every other CTA off its schedulers) */
 #define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */

@@ -57,12 +57,21 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// A transfer that never lands would be a bug in this file; rather than hang the GPU, a wait that has lasted more
-// than five seconds of wall time (globaltimer, checked every 4096 failed attempts) traps.
+// A transfer that never lands would be a bug in this file (or a launch that lost the co-residency it relies on); rather
+// than hang the GPU - or trap, which would poison the context of every engine in the process - a wait that has lasted
+// more than five seconds of wall time (globaltimer, checked every 4096 failed attempts) latches an error word and the
+// thread leaves the kernel; the threads that depended on it time out the same way. The host mirrors the word behind
+// every forward launch group and reports it from the next synchronising call.
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+__device__ int g_wait_timeout;  // 0, or which kind of bounded wait expired on this device (1 mbarrier, 2 frame counter)
+__device__ __noinline__ void wait_timed_out(int code) {
+    atomicCAS(&g_wait_timeout, 0, code);
+    __threadfence();
+    asm volatile("exit;");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -71,7 +80,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if ((spins & 4095u) == 0) {
             const unsigned long long now = global_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 5000000000ull) __trap();
+            else if (now - t0 > 5000000000ull) wait_timed_out(1);
         }
     }
 }
@@ -447,7 +456,7 @@ struct GroupSync {
     int g;
     __device__ __forceinline__ void operator()() const { group_sync(g); }
 };
-// spin until *counter >= target (acquire); a counter that never gets there is a bug: trap after five seconds
+// spin until *counter >= target (acquire); a counter that never gets there is a bug: give up after five seconds
 __device__ __forceinline__ void wait_counter(const unsigned *counter, unsigned target) {
     unsigned long long t0 = 0;
     for (unsigned spins = 1;; spins++) {
@@ -458,7 +467,7 @@ __device__ __forceinline__ void wait_counter(const unsigned *counter, unsigned t
         if ((spins & 1023u) == 0) {
             const unsigned long long now = global_ns();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 5000000000ull) __trap();
+            else if (now - t0 > 5000000000ull) wait_timed_out(2);
         }
     }
 }

@@ -40,7 +40,7 @@ def test_forward_variants_bit_identical(gpu_required):
     F = 8
     eng, torch, B = _device_engine(cfg, F, 12)
     defaults = {B.OPT_FUSED_PYRAMID: -1, B.OPT_TMA: 2, B.OPT_PACKED_MATH: 1, B.OPT_FWD_LANES: 1, B.OPT_FWD_SUB_FRAMES: 64,
-                B.OPT_PASS1_ORDER: 0, B.OPT_PYRAMID_LAG: 2, B.OPT_PASS1_SPLIT: 2, B.OPT_FWD_SMS: 0, B.OPT_STREAM_LAG1: 2,
+                B.OPT_PASS1_ORDER: 0, B.OPT_PYRAMID_LAG: 2, B.OPT_PASS1_SPLIT: 16, B.OPT_FWD_SMS: 0, B.OPT_STREAM_LAG1: 2,
                 B.OPT_STREAM_LAG2: 4, B.OPT_STREAM_RING: 5}
     variants = [
         {},
@@ -59,7 +59,8 @@ def test_forward_variants_bit_identical(gpu_required):
         {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 3},
         {B.OPT_TMA: 3, B.OPT_PYRAMID_LAG: 8},          # lag >= frames: every block is produced by the tail loop
         {B.OPT_TMA: 3, B.OPT_FWD_LANES: 2, B.OPT_FWD_SUB_FRAMES: 2},
-        {B.OPT_PASS1_SPLIT: 8},                        # finer pass-1 work units
+        {B.OPT_PASS1_SPLIT: 2},                        # coarser pass-1 work units (two CTAs per column tile)
+        {B.OPT_PASS1_SPLIT: 5},
         {B.OPT_FWD_SMS: 100},                          # pass-2 grid sized for fewer SMs
         {B.OPT_PACKED_MATH: 3},                        # table-driven quantiser for levels 0..2
         {B.OPT_TMA: 4},                                # all three stages in one persistent dataflow-scheduled launch

@@ -6,7 +6,7 @@ import torch
 from phantomsdr_b200 import SpectrumConfig
 from phantomsdr_b200.backend import (B200FFT, OPT_STAGE_MASK, OPT_FUSED_PYRAMID, OPT_TMA, OPT_PACKED_MATH, OPT_FWD_LANES,
                                      OPT_FWD_SUB_FRAMES, OPT_PASS1_ORDER, OPT_PYRAMID_LAG, OPT_STREAM_GRID, OPT_STREAM_LAG1,
-                                     OPT_STREAM_LAG2, OPT_STREAM_RING)
+                                     OPT_STREAM_LAG2, OPT_STREAM_RING, OPT_PASS1_SPLIT)
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 H = 64
@@ -24,7 +24,7 @@ ring.normal_(0, 1e-3)
 torch.cuda.synchronize()
 
 DEFAULTS = {OPT_FUSED_PYRAMID: -1, OPT_PYRAMID_LAG: 2, OPT_TMA: 2, OPT_PACKED_MATH: 1, OPT_FWD_LANES: 1, OPT_FWD_SUB_FRAMES: 64, OPT_PASS1_ORDER: 0,
-            OPT_STREAM_GRID: 0, OPT_STREAM_LAG1: 2, OPT_STREAM_LAG2: 4, OPT_STREAM_RING: 5}
+            OPT_STREAM_GRID: 0, OPT_STREAM_LAG1: 2, OPT_STREAM_LAG2: 4, OPT_STREAM_RING: 5, OPT_PASS1_SPLIT: 16}
 
 
 def configure(opts):
@@ -59,11 +59,16 @@ def t(mask, reps=10):
 VARIANTS = [
     ("default (tma2 fuse0)", {}),
     ("scalar quantiser", {OPT_PACKED_MATH: 0}),
+    ("pass-1 split 2", {OPT_PASS1_SPLIT: 2}),
     ("tma1 two-CTA pass 2", {OPT_TMA: 1}),
     ("power plane (fuse 2)", {OPT_FUSED_PYRAMID: 2}),
     ("pass-1 order 1", {OPT_PASS1_ORDER: 1}),
     ("pass-1 order 2", {OPT_PASS1_ORDER: 2}),
     ("2 lanes x 4 frames", {OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 4}),
+    ("2 lanes x 32 frames", {OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 32}),
+    ("2 lanes x 16 frames", {OPT_FWD_LANES: 2, OPT_FWD_SUB_FRAMES: 16}),
+    ("4 lanes x 16 frames", {OPT_FWD_LANES: 4, OPT_FWD_SUB_FRAMES: 16}),
+    ("3 lanes x 8 frames", {OPT_FWD_LANES: 3, OPT_FWD_SUB_FRAMES: 8}),
     ("sub-batches of 8", {OPT_FWD_SUB_FRAMES: 8}),
     ("tma3 fused lag1", {OPT_TMA: 3, OPT_PYRAMID_LAG: 1}),
     ("tma3 fused lag2", {OPT_TMA: 3, OPT_PYRAMID_LAG: 2}),
