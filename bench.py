@@ -436,7 +436,8 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
     eng = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, cfg.brightness_offset, device=local)
     eng.set_output_additional_size(n)
     eng.plan_r2c() if cfg.is_real else eng.plan_c2c()
-    HR = max(H, 2 * F + 2)  # the block-streaming e2e path keeps two blocks of halves (+ the shared older half) resident
+    E2E_DEPTH = 4  # host blocks in flight in the e2e path: the hop ring keeps that many blocks of halves (+ the shared older half)
+    HR = max(H, E2E_DEPTH * F + 2)
     eng.set_hop_ring(HR)
     eng.set_batch_frames(F)
     eng.set_pipeline(args.banks)
@@ -746,7 +747,7 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
         eng.sync()
         rs = np.random.default_rng(0x5EED + 3 + rank)
         sets = []
-        for _ in range(2):  # two blocks in flight -> two sets of pinned host buffers
+        for _ in range(E2E_DEPTH):  # blocks in flight -> as many sets of pinned host result buffers
             sets.append(dict(pcm=eng.pinned(pcm_bytes * F * args.clients * h, np.uint8),
                              pwr=eng.pinned(4 * F * args.clients, np.float32),
                              valid=eng.pinned(F * args.clients, np.uint8),
@@ -759,8 +760,9 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
             halves_sets = []
             for _ in range(2):
                 halves = []
+                blockbuf = eng.pinned(F * cfg.hop_floats * np.dtype(dt).itemsize, dt)  # a block's halves back to back
                 for _k in range(F):
-                    hb = eng.pinned(cfg.hop_floats * np.dtype(dt).itemsize, dt)
+                    hb = blockbuf[_k * cfg.hop_floats:(_k + 1) * cfg.hop_floats]
                     if dt == np.float32:
                         hb[:] = (rs.standard_normal(cfg.hop_floats) * 1e-3).astype(np.float32)
                     elif dt == np.int16:
@@ -774,11 +776,11 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
         def e2e_run(halves_sets, prime, blocks, f0):
             eng.stream_prime(prime)
             for k in range(blocks):
-                st = sets[k & 1]
-                if k >= 2:
-                    eng.wait_block()  # block k-2 used this buffer set
+                st = sets[k % E2E_DEPTH]
+                if k >= E2E_DEPTH:
+                    eng.wait_block()  # block k - depth used this buffer set
                 eng.submit_block(halves_sets[k & 1], f0 + k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
-            for _ in range(min(2, blocks)):
+            for _ in range(min(E2E_DEPTH, blocks)):
                 eng.wait_block()
 
         def e2e_measure(dt):
@@ -790,7 +792,7 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
 
         dt = e2e_measure(np.float32)
         common = f"-> forward FFT + pyramid (every {wf_skip} frame(s)) -> clients -> D2H of the int8 pyramids and " \
-                 f"{'int16' if args.pcm16 else 'int32'} PCM / pwr / valid of every frame; two blocks in flight"
+                 f"{'int16' if args.pcm16 else 'int32'} PCM / pwr / valid of every frame; four blocks in flight"
         e2e = {"value": nblk * F * cfg.hop_samples / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": cfg.hop_floats * 4 * H, "d2h_bytes_per_step": int(dbytes_frame * H),
                "frames_timed": nblk * F,

@@ -259,8 +259,9 @@ int b200_clients_read_pre_dc(b200_engine *e, float *out);
 /* ------------------------------------------------------------------------------------------
  * Pipelined block form of the same host-buffer path: load -> execute -> signal_loop for `nframes` frames per
  * call, with the host->device copy of block k+1, the kernels of block k and the device->host copy of block
- * k's results running on three streams (up to two blocks in flight). Needs b200_set_batch_frames(F),
- * b200_set_pipeline(>= 2) and a hop ring of >= 2F+2 halves.
+ * k's results running on three streams. Up to min(4, (ring halves - 2) / F) blocks may be in flight: needs
+ * b200_set_batch_frames(F), b200_set_pipeline(>= 2) and a hop ring of >= 2F+2 halves (4F+2 for four blocks, which keeps
+ * the host->device link busy back to back: measured 39.5 -> ? GB/s at cfg 2).
  *   b200_stream_prime(older_half)     : the half that precedes the first frame (the reference reads two halves
  *                                       before its first transform, src/fft.cpp:50-67)
  *   b200_submit_block(new_halves[nframes], ...): frame f of the block = (previous newest half | new_halves[f]);

@@ -123,10 +123,13 @@ static_assert(TmaSmem::kStage >= sizeof(float2) * 32 * TmaSmem::kRow2, "stage mu
 // ------------------------------------------------------------------------------------------------
 // pass 1: grid = (N2/T) * nsplit CTAs. CTA (tile, part) handles the frames f == part (mod nsplit) of column tile
 // `tile`; block = 256 consumers + 1 producer warp.
-//   ring_map  : hop ring as a 2-D uint32 tensor {2*N2, nhops*N1/2}, box {2*T, 256}
+//   ring_map  : hop ring as a 2-D tensor of N2 elements per row, nhops*N1/2 rows, box {T elements, 256 rows}; an element (an
+//               IQ sample, or two consecutive real samples) is EB bytes: 8 = float pair (mapped as 2 uint32), 4 = 16-bit
+//               pair (uint32), 2 = 8-bit pair (uint16) - raw ADC samples are converted here exactly as
+//               SampleConverter<T>::read does (src/samplereader.cpp:29-40,59-66; load_sample in fft_fwd.cuh)
 //   window_map: Hann window as {N2 (c2c) | 2*N2 (r2c), N1}, box {T | 2*T, 256}
 // ------------------------------------------------------------------------------------------------
-template <bool REAL>
+template <bool REAL, int EB = 8>
 __global__ void __launch_bounds__(kTmaThreads, 2)
     fft_pass1_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap ring_map,
                          const __grid_constant__ CUtensorMap window_map, int nframes, int order, int nsplit) {
@@ -189,13 +192,15 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
 
     // thread 0 drives TMA: the window slice of a column tile when it changes (c2c), and one item ahead of the consumers
     auto issue_item = [&](int tile, int f) {
-        mbar_expect_tx(full, sizeof(float2) * N1 * T);
+        mbar_expect_tx(full, EB * N1 * T);
         const int hopA = (p.hop0 + f) % p.nhops, hopB = (p.hop0 + f + 1) % p.nhops;
         // rows 0..511 of the frame come from the older hop, 512..1023 from the newer one
-        tma_load_2d(smem_raw + 0 * 16384, &ring_map, tile * T * 2, hopA * (N1 / 2), full);
-        tma_load_2d(smem_raw + 1 * 16384, &ring_map, tile * T * 2, hopA * (N1 / 2) + 256, full);
-        tma_load_2d(smem_raw + 2 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2), full);
-        tma_load_2d(smem_raw + 3 * 16384, &ring_map, tile * T * 2, hopB * (N1 / 2) + 256, full);
+        constexpr int kBox = EB * 256 * T;                  // bytes of one box of 256 rows
+        const int x0 = tile * T * (EB == 8 ? 2 : 1);        // (a float pair is two elements of the uint32 map)
+        tma_load_2d(smem_raw + 0 * kBox, &ring_map, x0, hopA * (N1 / 2), full);
+        tma_load_2d(smem_raw + 1 * kBox, &ring_map, x0, hopA * (N1 / 2) + 256, full);
+        tma_load_2d(smem_raw + 2 * kBox, &ring_map, x0, hopB * (N1 / 2), full);
+        tma_load_2d(smem_raw + 3 * kBox, &ring_map, x0, hopB * (N1 / 2) + 256, full);
     };
     auto issue_window = [&](int tile) {
         if constexpr (!REAL) {
@@ -252,9 +257,22 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
         }
         mbar_wait(full, it_local & 1);
         float2 v[RA];
+        // raw ADC samples: (x ^ topbit) as signed, / 2^(bits-1) (an exact multiply)
+        const unsigned flip = (p.in_format == FMT_U16) ? 0x8000u : (p.in_format == FMT_U8) ? 0x80u : 0u;
 #pragma unroll
         for (int j = 0; j < RA; j++) {
-            float2 x = sm[(r + RB * j) * T + c];
+            float2 x;
+            if constexpr (EB == 8) {
+                x = sm[(r + RB * j) * T + c];
+            } else if constexpr (EB == 4) {
+                const unsigned w = reinterpret_cast<const unsigned *>(smem_raw)[(r + RB * j) * T + c];
+                x.x = (float)(short)((w & 0xFFFFu) ^ flip) * (1.0f / 32768.0f);
+                x.y = (float)(short)((w >> 16) ^ flip) * (1.0f / 32768.0f);
+            } else {
+                const unsigned w = reinterpret_cast<const unsigned short *>(smem_raw)[(r + RB * j) * T + c];
+                x.x = (float)(signed char)((w & 0xFFu) ^ flip) * (1.0f / 128.0f);
+                x.y = (float)(signed char)((w >> 8) ^ flip) * (1.0f / 128.0f);
+            }
             if constexpr (REAL) {
                 const float2 tab = reinterpret_cast<const float2 *>(win)[r + RB * j];
                 x.x *= fmaf(tab.y, sB0, fmaf(-tab.x, cB0, 0.5f));

@@ -10,11 +10,11 @@ from helpers import make_engine, hop_as_floats
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("is_real", [False, True])
-def test_block_streaming_equals_per_frame_calls(gpu_required, is_real):
+@pytest.mark.parametrize("is_real,depth", [(False, 2), (True, 2), (False, 3), (False, 4)])
+def test_block_streaming_equals_per_frame_calls(gpu_required, is_real, depth):
     cfg = SpectrumConfig(sps=4_370_000 * (2 if is_real else 1), fft_size=(1 << 18) if is_real else (1 << 17), is_real=is_real)
     n, h = cfg.audio_fft_size, cfg.audio_fft_size // 2
-    F, nblocks, nc = 4, 3, 12
+    F, nblocks, nc = 4, 3 if depth == 2 else 7, 12   # (depth = blocks in flight = what the hop ring holds)
     src = SignalSource(cfg, seed=21)
     hops = [hop_as_floats(src.next_hop()).copy() for _ in range(F * nblocks + 1)]
     specs = make_clients(cfg, nc, modes=(USB, LSB, AM, FM), tones=[src.display_bin(t) for t in src.tones])
@@ -42,13 +42,18 @@ def test_block_streaming_equals_per_frame_calls(gpu_required, is_real):
 
     # pipelined blocks
     b = make_engine(cfg)
-    b.set_hop_ring(2 * F + 2)
+    b.set_hop_ring(depth * F + 2)
     b.set_batch_frames(F)
     b.set_pipeline(2)
     setup(b)
     sets = []
-    for _ in range(2):
-        sets.append(dict(halves=[b.malloc(cfg.hop_floats) for _ in range(F)], pcm=b.pinned(4 * F * nc * h, np.int32),
+    for _ in range(depth):
+        if depth == 4:  # a block's halves in one host buffer: the engine merges them into one copy per contiguous run
+            blockbuf = b.malloc(F * cfg.hop_floats)
+            halves = [blockbuf[f * cfg.hop_floats:(f + 1) * cfg.hop_floats] for f in range(F)]
+        else:
+            halves = [b.malloc(cfg.hop_floats) for _ in range(F)]
+        sets.append(dict(halves=halves, pcm=b.pinned(4 * F * nc * h, np.int32),
                          pwr=b.pinned(4 * F * nc, np.float32), valid=b.pinned(F * nc, np.uint8),
                          pyr=b.pinned(F * b.pyramid_bytes, np.int8)))
     prime = b.malloc(cfg.hop_floats)
@@ -61,18 +66,18 @@ def test_block_streaming_equals_per_frame_calls(gpu_required, is_real):
         got_pyr.extend(st["pyr"].reshape(F, -1).copy())
 
     for k in range(nblocks):
-        st = sets[k & 1]
-        if k >= 2:
+        st = sets[k % depth]
+        if k >= depth:
             b.wait_block()
-            collect(sets[k & 1])
+            collect(sets[k % depth])
         for f in range(F):
             st["halves"][f][:] = hops[1 + k * F + f]
         b.submit_block(st["halves"], k * F, st["pcm"], st["pwr"], st["valid"], st["pyr"])
     # drain in submission order
-    pending = list(range(max(0, nblocks - 2), nblocks))
+    pending = list(range(max(0, nblocks - depth), nblocks))
     for k in pending:
         b.wait_block()
-        collect(sets[k & 1])
+        collect(sets[k % depth])
     b.close()
     assert len(got_pcm) == F * nblocks
     for f in range(F * nblocks):

@@ -153,3 +153,45 @@ def test_chunked_demodulation_equals_sequential(gpu_required):
             assert np.array_equal(pa, pb), f"chunk {chunk} frame {f}: PCM differs at clients {np.flatnonzero((pa != pb).any(axis=1))[:8]}"
             assert np.array_equal(wa.view(np.uint32), wb.view(np.uint32)), f"chunk {chunk} frame {f}: pwr differs"
     assert any(p.any() for p, _, _ in ref[3 * F:]), "AGC never opened: test is vacuous"
+
+
+@pytest.mark.parametrize("is_real", [False, True])
+def test_raw_sample_formats_on_the_tma_path(gpu_required, is_real):
+    """2^20-point transforms read raw ADC samples through the TMA pass 1 (SampleConverter fused): the
+    result must be bit-identical to the float path fed with the converted samples ((x ^ topbit) / 2^(bits-1),
+    src/samplereader.cpp:29-40,59-66)."""
+    import torch
+
+    from phantomsdr_b200 import backend as B
+
+    cfg = SpectrumConfig(sps=70_000_000, fft_size=1 << 21, is_real=True) if is_real else SpectrumConfig(sps=35_000_000, fft_size=1 << 20)
+    F, H = 4, 6
+    g = torch.Generator(device="cuda")
+    g.manual_seed(77)
+    per_hop = cfg.hop_floats  # scalar samples per hop
+    cases = [(B.FMT_U8, torch.uint8, 8), (B.FMT_S8, torch.int8, 8), (B.FMT_U16, torch.int16, 16), (B.FMT_S16, torch.int16, 16)]
+    for fmt, tdt, bits in cases:
+        raw = torch.randint(0, 1 << bits, (H * per_hop,), generator=g, device="cuda", dtype=torch.int32)
+        # the float the reference's converter makes of each raw value
+        unsigned = fmt in (B.FMT_U8, B.FMT_U16)
+        signed = (raw ^ (1 << (bits - 1))) if unsigned else raw
+        signed = torch.where(signed >= (1 << (bits - 1)), signed - (1 << bits), signed)
+        as_float = signed.to(torch.float32) / float(1 << (bits - 1))
+        out = []
+        for use_raw in (True, False):
+            eng = make_engine(cfg)
+            eng.set_option(B.OPT_INPUT_FORMAT, fmt if use_raw else B.FMT_F32)
+            eng.set_hop_ring(H)
+            eng.set_batch_frames(F)
+            ring = torch.as_tensor(eng.device_hop_ring(H), device="cuda").reshape(-1)  # (allocated for float samples)
+            if use_raw:  # raw hops are packed back to back from the start of the ring
+                view = ring.view(torch.uint8) if bits == 8 else ring.view(torch.int16)
+                view[: H * per_hop] = raw.to(torch.uint8) if bits == 8 else raw.to(torch.int16)
+            else:
+                ring[: H * per_hop] = as_float
+            torch.cuda.synchronize()
+            out.append(_snapshot(eng, torch, F, hop0=1))
+            eng.close()
+        assert float(out[0][0].abs().max()) > 0
+        assert torch.equal(out[0][0], out[1][0]), f"format {fmt}: spectrum differs from the float path"
+        assert torch.equal(out[0][1], out[1][1]), f"format {fmt}: pyramid differs from the float path"
