@@ -9,3 +9,4 @@ run cfg3 --config cfg3
 run cfg1 --config cfg1
 run cadence_pcm16 --waterfall-skip 0 --pcm16 --no-cpu-baseline
 run raw_s16 --e2e-raw s16 --waterfall-skip 0 --pcm16 --no-cpu-baseline
+run raw_u8 --e2e-raw u8 --waterfall-skip 0 --pcm16 --no-cpu-baseline

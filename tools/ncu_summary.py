@@ -26,7 +26,10 @@ STALLS = "smsp__pcsamp_warps_issue_stalled_"
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):  # already exported (ncu -i report --page raw --csv) on the GPU box
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     r = list(csv.reader(io.StringIO(out)))
     head, units = r[0], r[1]
     return head, units, r[2:]
