@@ -23,7 +23,7 @@ from phantomsdr_b200.synth import SignalSource, make_clients  # noqa: E402
 def make(cfg, dev, F, nhops):
     e = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, 0, dev)
     e.set_output_additional_size(cfg.audio_fft_size)
-    e.plan_c2c()
+    e.plan_r2c() if cfg.is_real else e.plan_c2c()
     e.set_hop_ring(nhops)
     e.set_batch_frames(F)
     e.set_pipeline(2)
@@ -36,7 +36,16 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
-    cfg = SpectrumConfig(sps=35_000_000, fft_size=1 << 20)
+    # c2c (BASELINE cfg 2 shape) and r2c (cfg 3 shape: the Hermitian-split kernel writes the spectrum and the peer copies)
+    for cfg in (SpectrumConfig(sps=35_000_000, fft_size=1 << 20), SpectrumConfig(sps=70_000_000, fft_size=1 << 21, is_real=True)):
+        exchange_case(cfg, local, dev, rank, world)
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_EXCHANGE_OK")
+    dist.destroy_process_group()
+
+
+def exchange_case(cfg, local, dev, rank, world):
     n, h, F, nb = cfg.audio_fft_size, cfg.audio_fft_size // 2, 4, 3
     nc = 24
     everyone = make_clients(cfg, nc * world, seed=77, modes=(USB, LSB, AM, FM))
@@ -77,8 +86,9 @@ def main():
                     lo = min(cfg.slice_offset(c.l) for c in blk)
                     iv = sorted((cfg.slice_offset(c.l), cfg.slice_offset(c.l) + c.r - c.l) for c in blk)
                     # two ranges: below / above the wrap point of the display axis
-                    low = [x for x in iv if x[0] < cfg.fft_size // 2]
-                    high = [x for x in iv if x[0] >= cfg.fft_size // 2]
+                    half = cfg.fft_result_size // 2
+                    low = [x for x in iv if x[0] < half]
+                    high = [x for x in iv if x[0] >= half]
                     r = [(min(a for a, _ in part), max(b for _, b in part)) if part else (0, 0) for part in (low, high)]
                     e.set_peer_ranges(g - 1, r[0][0], r[0][1], r[1][0], r[1][1])
                 if mode == "scatter-dma":
@@ -134,11 +144,7 @@ def main():
     for mode in ("broadcast", "scatter", "scatter-dma"):
         got = run(mode)
         for f, (a, b) in enumerate(zip(ref, got)):
-            assert np.array_equal(a, b), f"rank {rank} mode {mode} frame {f}: PCM differs"
-    dist.barrier()
-    if rank == 0:
-        print("MGPU_EXCHANGE_OK")
-    dist.destroy_process_group()
+            assert np.array_equal(a, b), f"rank {rank} {'r2c' if cfg.is_real else 'c2c'} mode {mode} frame {f}: PCM differs"
 
 
 if __name__ == "__main__":
