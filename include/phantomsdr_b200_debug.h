@@ -35,6 +35,8 @@ extern "C" {
 #define B200_OPT_PASS1_SPLIT 22  /* CTAs per column tile of the TMA pass 1 (default 16 = work units of four frames at 64 frames per launch) */
 #define B200_OPT_DEMOD_GENERIC 23 /* comparison aid: 1 = run-time-plan demodulation kernel even for audio_fft_size 360 */
 #define B200_OPT_TAIL_SMEM_KB 24 /* shared memory a tail-pipeline CTA asks for (default 224 KB = the whole SM: keeps every other CTA off its schedulers) */
+#define B200_OPT_R2C_SPLIT_KERNEL 25 /* r2c: 1 (default) = Hermitian split in a streaming kernel of its own, then the c2c pyramid kernel on
+                                      * the send frames; 0 = split and quantiser in one kernel (bit-identical, measured slower) */
 #define B200_OPT_STREAM_GRID 14  /* B200_OPT_TMA 4: CTAs of the stream kernel (0 = one per SM) */
 #define B200_OPT_STREAM_LAG1 15  /* ... frame slots between pass 1 and pass 2 of a frame in the item order (default 2) */
 #define B200_OPT_STREAM_LAG2 16  /* ... between pass 1 and the quantiser (default 4) */

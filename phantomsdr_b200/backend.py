@@ -31,6 +31,7 @@ OPT_FWD_SMS = 21
 OPT_PASS1_SPLIT = 22
 OPT_DEMOD_GENERIC = 23
 OPT_TAIL_SMEM_KB = 24
+OPT_R2C_SPLIT_KERNEL = 25
 _PUBLIC_OPTIONS = {OPT_RELOAD_BOTH, OPT_HOST_MIRROR, OPT_INPUT_FORMAT, OPT_PEER_STORES, OPT_PCM16}  # include/phantomsdr_b200.h
 _FMT_OF_DTYPE = {"float32": FMT_F32, "uint8": FMT_U8, "int8": FMT_S8, "uint16": FMT_U16, "int16": FMT_S16}
 

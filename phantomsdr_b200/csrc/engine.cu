@@ -258,6 +258,7 @@ struct b200_engine {
     int flag_waits = 0;                 // b200_enqueue_wait calls since stream_check last read the flag error word
     int opt_tail_smem_kb = 224;         // shared memory a tail CTA asks for: with its 3 KB of static memory exactly the SM's 227 KB,
                                         // so that no other CTA (not even a pyramid CTA with 1 KB) shares its schedulers
+    int opt_r2c_split = 1;              // r2c: Hermitian split as its own streaming kernel + the c2c pyramid kernel (0: one kernel)
     int opt_demod_generic = 0;          // 1: never use the compile-time-size demodulation kernel (comparison aid)
     int demod_wpc = 0;                  // warps per CTA of client_demod_warp_kernel (0 = audio FFT too long: sequential kernel)
     int cstate = 0;                     // which copy of the overlap state the next client batch reads
@@ -828,7 +829,15 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         // r2c: the kernel also does the Hermitian split, so it covers every frame and drops the pyramid of the frames
         // between two sends itself; c2c: only the send frames are launched
         int pyr_frames = frames;
-        if (!e->is_real && wf_skip > 1) {
+        const bool split_first = e->is_real && e->opt_r2c_split && (e->R % 1024) == 0;
+        if (split_first) {  // r2c: the Hermitian split of every frame as a streaming kernel of its own
+            dim3 sgrid((unsigned)(e->R / 1024), frames);
+            r2c_split_kernel<<<sgrid, 256, 0, e->stream>>>(q);
+            e->launches++;
+            CU(cudaGetLastError());
+            q.natural = 1;
+        }
+        if ((!e->is_real || split_first) && wf_skip > 1) {
             q.frame0 = wf_first;
             q.frame_step = wf_skip;
             pyr_frames = wf_count;
@@ -836,7 +845,7 @@ int forward_range(b200_engine *e, long hop0, int f0, int frames, int lane) {
         if (pyr_frames > 0) {
             dim3 grid((unsigned)((e->R >> q.base_level) / (256 * per)), pyr_frames);
             const bool pk = e->opt_packed & 1;
-            if (e->is_real) {
+            if (e->is_real && !split_first) {
                 if (pk) pyramid_kernel<PYR_R2C, 16, true><<<grid, 256, 0, e->stream>>>(q);
                 else pyramid_kernel<PYR_R2C, 16, false><<<grid, 256, 0, e->stream>>>(q);
             } else if (fuse == 1) {
@@ -1533,6 +1542,7 @@ int b200_debug_option(b200_engine *e, int option, int value) {
         e->opt_sub_frames = value;
         return 0;
     case B200_OPT_DEMOD_GENERIC: e->opt_demod_generic = value ? 1 : 0; return 0;
+    case B200_OPT_R2C_SPLIT_KERNEL: e->opt_r2c_split = value ? 1 : 0; return 0;
     case B200_OPT_TAIL_SMEM_KB:
         if (value < 0 || value > 224) return fail(B200_EINVAL, "tail shared memory must be 0..224 KB");
         e->opt_tail_smem_kb = value;

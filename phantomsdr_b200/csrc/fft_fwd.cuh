@@ -498,6 +498,7 @@ struct PyrParams {
     unsigned peer_lo[kMaxPeers][2], peer_hi[kMaxPeers][2];  // PYR_R2C: bins each peer needs (two half-open ranges), as FwdParams
     int frame0, frame_step;  // the launch covers frames frame0, frame0 + frame_step, ... (blockIdx.y-th of them)
     int wf_first, wf_skip;   // PYR_R2C (every frame is split): only frames wf_first, wf_first + wf_skip, ... get a pyramid
+    int natural;             // PYR_SPEC: 1 = display bin d is FFT bin d (r2c), 0 = the IQ shift below
     const uint2 *qtab;       // optional [3][2048] quantiser tables of levels 0..2 (see quantize_table), or nullptr
 };
 
@@ -592,7 +593,7 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
     if constexpr (MODE == PYR_SPEC) {
         // display bin d <-> FFT bin (d + R/2 + 1) mod R   (src/fft_impl.cpp:148-160)
         const float2 *spec = p.spec + (size_t)frame * p.spec_stride;
-        const unsigned k0 = (d0 + (R >> 1) + 1) & (R - 1);
+        const unsigned k0 = p.natural ? d0 : ((d0 + (R >> 1) + 1) & (R - 1));
         // d0 is a multiple of PER, so the thread's PER bins start at k0 == 1 (mod PER): with the engine's buffer offset
         // (bin 1 on a 128-byte line) that is an aligned, contiguous run - 128-bit loads, except for the one thread
         // whose run wraps past bin R-1 and for externally bound, unaligned buffers
@@ -721,6 +722,77 @@ __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int fram
         if (p.wf_skip > 1 && (frame < p.wf_first || (frame - p.wf_first) % p.wf_skip != 0)) return;
     }
     pyramid_tree<PER, PK, TB>(p, frame, blk, tid, pw, B, warp_sum_s, sync);
+}
+
+// r2c Hermitian split on its own: X[k] for four bins per thread, the arithmetic of the PYR_R2C branch above expression for
+// expression (same twiddle decomposition W^(16 j) * W^i), so the spectrum is bit-identical; a streaming kernel at 40
+// registers whose loads, unlike those of the 80-register split-and-quantise kernel, are hidden by occupancy. The pyramid
+// then comes from pyramid_kernel<PYR_SPEC> with p.natural = 1 - on the send frames only.
+__global__ void __launch_bounds__(256) r2c_split_kernel(const PyrParams p) {
+    const unsigned R = 1u << p.log2R;
+    const int frame = p.frame0 + (int)blockIdx.y * p.frame_step;
+    const unsigned d0 = (blockIdx.x * 256u + threadIdx.x) * 4u;
+    float2 *spec = p.spec + (size_t)frame * p.spec_stride;
+    const float2 *Z = p.Z + (size_t)frame * R;
+    float2 a[4], b[4];
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(Z + d0);
+        const float4 x0 = src[0], x1 = src[1];
+        a[0] = make_float2(x0.x, x0.y);
+        a[1] = make_float2(x0.z, x0.w);
+        a[2] = make_float2(x1.x, x1.y);
+        a[3] = make_float2(x1.z, x1.w);
+    }
+    if (d0 == 0) {  // the run that pairs with bins 0 .. 3 wraps: Z[0], Z[R-1], Z[R-2], Z[R-3]
+        b[0] = Z[0];
+        b[1] = Z[R - 1];
+        b[2] = Z[R - 2];
+        b[3] = Z[R - 3];
+    } else {
+        const float2 *m = Z + (R - d0 - 3);  // ascending m[0 .. 3] = Z[R-d0-3 .. R-d0], b[i] = m[3 - i]; m + 1 is 16-byte aligned
+        b[3] = m[0];
+        const float4 x = *reinterpret_cast<const float4 *>(m + 1);
+        b[2] = make_float2(x.x, x.y);
+        b[1] = make_float2(x.z, x.w);
+        b[0] = m[3];
+    }
+    const unsigned base16 = d0 & ~15u, i0 = d0 & 15u;
+    const float2 w0 = cmul(__ldg(p.TLr + (base16 & 1023)), __ldg(p.THr + (base16 >> 10)));
+    float2 xs[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 e = make_float2(a[i].x + b[i].x, a[i].y - b[i].y);
+        const float2 o = make_float2(a[i].x - b[i].x, a[i].y + b[i].y);
+        const float2 w = (i0 + i == 0) ? w0 : cmul(w0, __ldg(p.TLr + i0 + i));
+        const float2 t = cmul(o, w);
+        float2 x = make_float2(0.5f * (e.x + t.y), 0.5f * (e.y - t.x));
+        x.x *= p.scale;
+        x.y *= p.scale;
+        xs[i] = x;
+    }
+    if (d0 == 0) {  // Nyquist bin, left unnormalised by the reference (src/fft_impl.cpp:152-154)
+        const float2 ny = make_float2(a[0].x - a[0].y, 0.f);
+        spec[R] = ny;
+        for (int pe = 0; pe < p.npeers; pe++)
+            if ((R >= p.peer_lo[pe][0] && R < p.peer_hi[pe][0]) || (R >= p.peer_lo[pe][1] && R < p.peer_hi[pe][1]))
+                (p.peers[pe] + (size_t)frame * p.spec_stride)[R] = ny;
+    }
+    if ((reinterpret_cast<uintptr_t>(spec + d0) & 15) == 0) {
+        float4 *dst = reinterpret_cast<float4 *>(spec + d0);
+        dst[0] = make_float4(xs[0].x, xs[0].y, xs[1].x, xs[1].y);
+        dst[1] = make_float4(xs[2].x, xs[2].y, xs[3].x, xs[3].y);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) spec[d0 + i] = xs[i];
+    }
+    for (int pe = 0; pe < p.npeers; pe++) {
+        float2 *ps = p.peers[pe] + (size_t)frame * p.spec_stride;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned k = d0 + i;
+            if ((k >= p.peer_lo[pe][0] && k < p.peer_hi[pe][0]) || (k >= p.peer_lo[pe][1] && k < p.peer_hi[pe][1])) ps[k] = xs[i];
+        }
+    }
 }
 
 // (the Hermitian-split mode is bound by the latency of its mirrored loads: three CTAs per SM instead of the two its 82 registers allow)

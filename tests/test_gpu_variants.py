@@ -195,3 +195,26 @@ def test_raw_sample_formats_on_the_tma_path(gpu_required, is_real):
         assert float(out[0][0].abs().max()) > 0
         assert torch.equal(out[0][0], out[1][0]), f"format {fmt}: spectrum differs from the float path"
         assert torch.equal(out[0][1], out[1][1]), f"format {fmt}: pyramid differs from the float path"
+
+
+@pytest.mark.parametrize("log2n", [17, 21])
+def test_r2c_split_kernel_equals_fused_split(gpu_required, log2n):
+    """r2c: the Hermitian split as a kernel of its own followed by the c2c pyramid kernel must give exactly the
+    spectrum (Nyquist bin included) and the pyramid of the one-kernel split-and-quantise path, with and without a
+    waterfall cadence."""
+    cfg = SpectrumConfig(sps=70_000_000 >> (21 - log2n), fft_size=1 << log2n, is_real=True)
+    F = 6
+    eng, torch, B = _device_engine(cfg, F, F + 2)
+    for skip in (1, 4):
+        eng.set_waterfall_cadence(skip)
+        res = []
+        for split in (0, 1):
+            eng.set_option(B.OPT_R2C_SPLIT_KERNEL, split)
+            eng.set_frame_number(2)
+            torch.as_tensor(eng.device_quantized(F), device="cuda").zero_()
+            res.append(_snapshot(eng, torch, F, hop0=1))
+        assert float(res[0][0].abs().max()) > 0
+        assert torch.equal(res[0][0], res[1][0]), f"cadence {skip}: spectrum differs"
+        assert torch.equal(res[0][1], res[1][1]), f"cadence {skip}: pyramid differs"
+        assert int((res[1][1] != 0).sum()) > 0
+    eng.close()
