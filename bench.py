@@ -630,8 +630,7 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
                     with torch.cuda.stream(copy_s):
                         if k >= 2:
                             copy_s.wait_event(ev_free[half])  # the forward group of block k - 2 read this region
-                        for f in range(F):
-                            ring_t[hop0 + 1 + f].copy_(host_in[half][f], non_blocking=True)
+                        ring_t[hop0 + 1:hop0 + 1 + F].copy_(host_in[half], non_blocking=True)  # one copy: F contiguous halves
                         ev_in[half].record(copy_s)
                     stream.wait_event(ev_in[half])
                 if k >= 2:
