@@ -417,6 +417,23 @@ def run_b200(args):
                            "ingest_msps": r["ingest_msps"], "ms_per_step": r["ms_per_step"],
                            "note": "fixed client total: the ingest rate rises with N until rank 0's forward group bounds it"},
             }
+        # untimed: the exchange step's own parity check (tests/mgpu_worker.py) in THIS process group - every rank's PCM on the
+        # spectrum delivered by each exchange mode against a local recomputation, c2c and r2c
+        verdict = "ok"
+        try:
+            sys.path.insert(0, str(ROOT / "tests"))
+            import mgpu_worker
+
+            for pcfg in mgpu_worker.CASES():
+                mgpu_worker.exchange_case(pcfg, local, dev, rank, world)
+        except Exception as exc:  # reported in the line, not raised: the measurements above stand on their own
+            verdict = f"FAILED: {exc!r}"[:300]
+        flags = [None] * world
+        dist.all_gather_object(flags, verdict)
+        if rank == 0:
+            bad = [f"rank {i}: {v}" for i, v in enumerate(flags) if v != "ok"]
+            line["mgpu"]["exchange_parity"] = ("PCM of every rank bit-identical to a local recomputation for NCCL broadcast, "
+                                               "fused peer stores and copy-engine scatter (c2c 2^20 and r2c 2^21)") if not bad else bad
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -30,6 +30,10 @@ def make(cfg, dev, F, nhops):
     return e
 
 
+def CASES():
+    return (SpectrumConfig(sps=35_000_000, fft_size=1 << 20), SpectrumConfig(sps=70_000_000, fft_size=1 << 21, is_real=True))
+
+
 def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -37,7 +41,7 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     # c2c (BASELINE cfg 2 shape) and r2c (cfg 3 shape: the Hermitian-split kernel writes the spectrum and the peer copies)
-    for cfg in (SpectrumConfig(sps=35_000_000, fft_size=1 << 20), SpectrumConfig(sps=70_000_000, fft_size=1 << 21, is_real=True)):
+    for cfg in CASES():
         exchange_case(cfg, local, dev, rank, world)
     dist.barrier()
     if rank == 0:
@@ -46,6 +50,8 @@ def main():
 
 
 def exchange_case(cfg, local, dev, rank, world):
+    # (failures are collected and raised at the end: every rank walks through the same collectives whatever it finds)
+    problems = []
     n, h, F, nb = cfg.audio_fft_size, cfg.audio_fft_size // 2, 4, 3
     nc = 24
     everyone = make_clients(cfg, nc * world, seed=77, modes=(USB, LSB, AM, FM))
@@ -111,7 +117,8 @@ def exchange_case(cfg, local, dev, rank, world):
                 else:
                     e.bank_acquire()
                 ex.broadcast(banks[bank])
-                assert ex.checksum_agrees(banks[bank])
+                if not ex.checksum_agrees(banks[bank]):
+                    problems.append(f"rank {rank} batch {k}: broadcast checksum differs")
             elif mode == "scatter-dma" and rank == 0:
                 e.execute_device(k * F, F)
                 if seq > 2:
@@ -131,10 +138,12 @@ def exchange_case(cfg, local, dev, rank, world):
                 e.enqueue_signal(True, [my_consumed], seq)
             for f in range(F):
                 pcm, pwr, valid = e.clients_fetch(f)
-                assert valid[:nc].all()
+                if not valid[:nc].all():
+                    problems.append(f"rank {rank} mode {mode} batch {k} frame {f}: invalid client frames")
                 out.append(pcm.copy())
         e.sync()
-        assert e.flag_error == 0
+        if e.flag_error != 0:
+            problems.append(f"rank {rank} mode {mode}: a peer flag wait timed out")
         if mode in ("scatter", "scatter-dma"):
             dist.barrier()
         e.close()
@@ -144,7 +153,11 @@ def exchange_case(cfg, local, dev, rank, world):
     for mode in ("broadcast", "scatter", "scatter-dma"):
         got = run(mode)
         for f, (a, b) in enumerate(zip(ref, got)):
-            assert np.array_equal(a, b), f"rank {rank} {'r2c' if cfg.is_real else 'c2c'} mode {mode} frame {f}: PCM differs"
+            if not np.array_equal(a, b):
+                problems.append(f"rank {rank} {'r2c' if cfg.is_real else 'c2c'} mode {mode} frame {f}: PCM differs")
+                break
+    dist.barrier()
+    assert not problems, problems[:4]
 
 
 if __name__ == "__main__":
