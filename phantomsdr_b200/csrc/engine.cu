@@ -229,6 +229,8 @@ struct b200_engine {
     int opt_peer_stores = 1;                // 1: FFT pass 2 stores into the peers itself; 0: b200_push_peers (copy engines)
     cudaEvent_t ev_push[4] = {}, ev_fwd_done = nullptr;
     bool push_pending[4] = {};
+    cudaStream_t peer_stream[kMaxPeers] = {};  // b200_push_peers: one copy stream per peer
+    cudaEvent_t ev_peer[kMaxPeers] = {};
     int *d_flag_err = nullptr;
 
     // clients
@@ -1391,6 +1393,12 @@ void b200_engine_destroy(b200_engine *e) {
         cudaStreamDestroy(e->tstream);
         cudaStreamDestroy(e->d2h_stream);
     }
+    for (int i = 0; i < kMaxPeers; i++)
+        if (e->peer_stream[i]) {
+            cudaStreamSynchronize(e->peer_stream[i]);
+            cudaEventDestroy(e->ev_peer[i]);
+            cudaStreamDestroy(e->peer_stream[i]);
+        }
     if (e->copy_stream) {
         cudaStreamSynchronize(e->copy_stream);
         for (int i = 0; i < b200_engine::kMaxBlocks; i++) {
@@ -1792,21 +1800,31 @@ int b200_push_peers(b200_engine *e, int nframes) {
         CU(cudaEventCreateWithFlags(&e->ev_fwd_done, cudaEventDisableTiming));
         for (int b = 0; b < 4; b++) CU(cudaEventCreateWithFlags(&e->ev_push[b], cudaEventDisableTiming));
     }
-    // the selected bank as the forward stream leaves it -> every peer's sub-band, by the copy engines
+    // the selected bank as the forward stream leaves it -> every peer's sub-band, by the copy engines. One stream per peer:
+    // on a single stream the seven pushes of an 8-GPU box ran one after the other (470 MB per 64-frame batch at one copy
+    // engine's rate, 1.2 ms - longer than the forward group) and bounded the ingest rate; the copy stream joins them, so
+    // whatever the caller enqueues there next (the "bank has landed" signal) still follows every push.
     CU(cudaEventRecord(e->ev_fwd_done, e->stream));
-    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_fwd_done, 0));
     const size_t bank_off = (size_t)e->cur_bank * e->batch * e->spec_stride;
     const float2 *src = e->d_spec + bank_off;
     const size_t pitch = e->spec_stride * sizeof(float2);
     for (int i = 0; i < e->npeers; i++) {
+        if (!e->peer_stream[i]) {
+            CU(cudaStreamCreateWithFlags(&e->peer_stream[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&e->ev_peer[i], cudaEventDisableTiming));
+        }
+        cudaStream_t ps = e->peer_stream[i];
+        CU(cudaStreamWaitEvent(ps, e->ev_fwd_done, 0));
         float2 *dst = e->peers[i] + bank_off;
         for (int j = 0; j < 2; j++) {
             size_t lo = e->peer_lo[i][j], hi = std::min<size_t>(e->peer_hi[i][j], e->spec_stride);
             if (hi <= lo) continue;
-            CU(cudaMemcpy2DAsync(dst + lo, pitch, src + lo, pitch, (hi - lo) * sizeof(float2), nframes, cudaMemcpyDeviceToDevice,
-                                 e->copy_stream));
+            CU(cudaMemcpy2DAsync(dst + lo, pitch, src + lo, pitch, (hi - lo) * sizeof(float2), nframes, cudaMemcpyDeviceToDevice, ps));
         }
+        CU(cudaEventRecord(e->ev_peer[i], ps));
+        CU(cudaStreamWaitEvent(e->copy_stream, e->ev_peer[i], 0));
     }
+    if (e->npeers == 0) CU(cudaStreamWaitEvent(e->copy_stream, e->ev_fwd_done, 0));
     CU(cudaEventRecord(e->ev_push[e->cur_bank], e->copy_stream));
     e->push_pending[e->cur_bank] = true;
     return 0;
