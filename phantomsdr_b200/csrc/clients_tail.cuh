@@ -86,7 +86,10 @@ __device__ __noinline__ bool t2_wait_slow(uint64_t *bar, unsigned parity, int *s
             const unsigned long long now = global_ns();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 2000000000ull) {
-                if (atomicCAS(s_abort, 0, 1) == 0) atomicCAS(err, 0, code);  // first stage to give up
+                if (atomicCAS(s_abort, 0, 1) == 0) {  // first stage of this CTA to give up; err is a mapped host word
+                    *reinterpret_cast<volatile int *>(err) = code;
+                    __threadfence_system();
+                }
                 return false;
             }
         }

@@ -210,7 +210,7 @@ struct b200_engine {
     CUtensorMap spec_map{};             // the spectrum as rows of 16 bins from bin 1, 128-byte swizzle (quantiser items)
     bool spec_map_ok = false;
     StreamSync *d_ssync = nullptr;
-    int *h_wait_err = nullptr;          // pinned mirror of g_wait_timeout (fft_tma.cuh)
+    int *h_wait_err = nullptr;          // the device's mapped bounded-wait error word (fft_tma.cuh: g_wait_err); not owned
     unsigned *h_abort = nullptr;        // pinned mirror of StreamSync::abort, refreshed behind every launch
     float2 *d_winT = nullptr;
     unsigned *d_items = nullptr;
@@ -252,7 +252,7 @@ struct b200_engine {
     int last_buf = 0;                   // buffer that holds the results of the last client batch
     bool use_tail2 = false;             // lane-per-client pipeline (clients_tail.cuh) with its own state layout
     Tail2State t2{};
-    int *h_tail_err = nullptr;          // pinned mirror of t2.err
+    int *h_tail_err = nullptr;          // mapped host word behind t2.err
     int last_client_frames = 0;
     int demod_fchunk = 1;
     int opt_client_mask = 3;            // profiling aid: bit0 = demodulation kernels, bit1 = tail kernel
@@ -443,6 +443,22 @@ int tma_prepare(b200_engine *e) {  // plan time: window map + kernel attributes
     if (e->log2M != 20) return 0;
     if (getenv("B200_NO_TMA")) return 0;
     if (!encode_tiled_fn()) return 0;  // no cuTensorMapEncodeTiled from this driver: the generic passes take over
+    {
+        // the word a bounded wait of the TMA kernels writes when it expires: one per device and process (mapped host memory
+        // behind a __device__ pointer), shared by every engine on the device and never freed
+        static int *host_word[64] = {};
+        if (e->device >= 0 && e->device < 64) {
+            if (!host_word[e->device]) {
+                int *h = nullptr, *d = nullptr;
+                CU(cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped));
+                *h = 0;
+                CU(cudaHostGetDevicePointer(&d, h, 0));
+                CU(cudaMemcpyToSymbol(g_wait_err, &d, sizeof(d)));
+                host_word[e->device] = h;
+            }
+            e->h_wait_err = host_word[e->device];
+        }
+    }
     CU(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
     if (!e->is_real) {
         int rc = make_map_2d(&e->window_map, e->d_window, kS, kS, kTmaT);
@@ -888,13 +904,6 @@ int run_forward_batch(b200_engine *e, long hop0, int frames);
 int run_forward(b200_engine *e, long hop0, int frames) {
     int rc = run_forward_batch(e, hop0, frames);
     if (!rc) e->fwd_frame += (uint64_t)frames;
-    if (!rc && e->tma_ok) {  // mirror the bounded-wait error word of the TMA kernels behind the launch group
-        if (!e->h_wait_err) {
-            CU(cudaHostAlloc(&e->h_wait_err, sizeof(int), cudaHostAllocDefault));
-            *e->h_wait_err = 0;
-        }
-        CU(cudaMemcpyFromSymbolAsync(e->h_wait_err, g_wait_timeout, sizeof(int), 0, cudaMemcpyDeviceToHost, e->stream));
-    }
     return rc;
 }
 int run_forward_batch(b200_engine *e, long hop0, int frames) {
@@ -1184,7 +1193,6 @@ int launch_tail2(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl)
     client_tail2_kernel<1><<<groups, kT2Threads, smem, e->tail_stream()>>>(ca, cl, e->t2, groups);
     e->launches++;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(e->h_tail_err, e->t2.err, sizeof(int), cudaMemcpyDeviceToHost, e->tail_stream()));
     return 0;
 }
 int launch_tail(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
@@ -1353,7 +1361,7 @@ void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_redo, e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax, e->t2.err,
+    void *dev[] = {e->d_redo, e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax,
                    e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
                    e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_qtab, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
                    e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
@@ -1366,7 +1374,6 @@ void b200_engine_destroy(b200_engine *e) {
     for (int i = 0; i < 2; i++)
         if (e->ev_fetch[i]) cudaEventDestroy(e->ev_fetch[i]);
     if (e->h_abort) cudaFreeHost(e->h_abort);
-    if (e->h_wait_err) cudaFreeHost(e->h_wait_err);
     if (e->d_wf_desc) cudaFree(e->d_wf_desc);
     if (e->d_wf_out) cudaFree(e->d_wf_out);
     if (e->h_wf_out) cudaFreeHost(e->h_wf_out);
@@ -1996,9 +2003,9 @@ int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int
         ALLOC0(t.ring, sizeof(float) * groups * t.NB * h * 32);
         ALLOC0(t.suf, sizeof(float) * groups * t.NB * h * 32);
         ALLOC0(t.cmax, sizeof(float) * groups * t.NB * 32);
-        ALLOC0(t.err, sizeof(int));
-        CU(cudaHostAlloc(&e->h_tail_err, sizeof(int), cudaHostAllocDefault));
+        CU(cudaHostAlloc(&e->h_tail_err, sizeof(int), cudaHostAllocMapped));  // written by the kernel only when a wait expires
         *e->h_tail_err = 0;
+        CU(cudaHostGetDevicePointer(&t.err, e->h_tail_err, 0));
     }
 #undef ALLOC0
     e->slots.assign(mc, ClientSlot{});
