@@ -27,8 +27,8 @@ extern "C" {
 #define B200_OPT_FWD_SUB_FRAMES 11 /* frames per forward launch group inside a device batch (default: the whole batch) */
 #define B200_OPT_PASS1_ORDER 12  /* tuning: work-item order of the TMA pass 1 (0 default: column tile sticky, frames swept together) */
 #define B200_OPT_PYRAMID_LAG 13  /* B200_OPT_TMA 3: frames between a pass-2 tile and the pyramid blocks that ride on it (default 2) */
-#define B200_OPT_DEMOD_CHUNK 19  /* frames per warp task of the frame-chunked demodulation kernel (default 8; 0 = the sequential
-                                   one-CTA-per-client kernel only). Results are bit-identical either way. */
+#define B200_OPT_DEMOD_CHUNK 19  /* frames per warp task of the frame-chunked demodulation kernel (default -1: chosen per launch from the
+                                   client count; 0 = the sequential one-CTA-per-client kernel only). Results are bit-identical either way. */
 #define B200_OPT_CLIENT_STAGE_MASK 20 /* profiling aid: bit0 = demodulation kernels, bit1 = tail kernel; default 3 */
 #define B200_OPT_FWD_SMS 21      /* SMs the persistent pass-2 kernel sizes its grid for (0 = all): with the tail kernel resident on
                                   * some SMs a one-CTA-per-SM grid would run in two waves */
