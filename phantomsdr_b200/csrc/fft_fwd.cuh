@@ -236,9 +236,11 @@ __device__ __forceinline__ int quantize_biased(float power, float bias) {
 __device__ __forceinline__ int quantize_dev(float power, int power_offset) {
     return quantize_biased(power, quant_bias(power_offset)) & 0xFF;
 }
-// Two bins per instruction on the sm_100 packed-f32 pipe where that keeps the reference's rounding: ptxas contracts
-// every mul.f32x2 -> add.f32x2 chain into FFMA2 (one rounding instead of two, even with explicit .rn and
-// -fmad=false), so the multiplies are packed (FMUL2) and each add that consumes a product stays scalar.
+// Two bins per instruction on the sm_100 packed-f32 pipe, keeping the reference's rounding: ptxas contracts every
+// mul.f32x2 -> add.f32x2 chain into FFMA2 (one rounding instead of two, even with explicit .rn and -fmad=false), so an
+// add that consumes a product is written as fma(product, 1, c) - round(round(a b) * 1 + c) is exactly the separately
+// rounded add, and with its multiplier slot taken ptxas leaves the FMUL2 in front of it alone (checked in the SASS:
+// FMUL2 followed by FFMA2 ..., R.F32 (= 1.0), c).
 __device__ __forceinline__ unsigned long long pk(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -258,9 +260,9 @@ __device__ __forceinline__ unsigned long long pk_add(unsigned long long a, unsig
     return d;
 }
 __device__ __forceinline__ unsigned long long pk_add_scalar(unsigned long long a, float c) {  // never fused with a producer
-    float x, y;
-    unpk(a, x, y);
-    return pk(__fadd_rn(x, c), __fadd_rn(y, c));
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(pk(1.f, 1.f)), "l"(pk(c, c)));
+    return d;
 }
 __device__ __forceinline__ void quantize2_biased(float p0, float p1, float bias, int &t0, int &t1) {
     const unsigned b0 = __float_as_uint(p0), b1 = __float_as_uint(p1);
@@ -273,10 +275,11 @@ __device__ __forceinline__ void quantize2_biased(float p0, float p1, float bias,
     unsigned long long v = pk_add(lv, t);  // both operands are sums: nothing to contract
     v = pk_mul(v, pk(0.3010299956639812f, 0.3010299956639812f));
     v = pk_mul(v, pk(20.f, 20.f));
+    v = pk_add_scalar(v, 127.f);
     float vx, vy;
     unpk(v, vx, vy);
-    t0 = __float2int_rz(fmaxf(__fadd_rn(vx, 127.f), -128.f));
-    t1 = __float2int_rz(fmaxf(__fadd_rn(vy, 127.f), -128.f));
+    t0 = __float2int_rz(fmaxf(vx, -128.f));
+    t1 = __float2int_rz(fmaxf(vy, -128.f));
 }
 // Table-driven form (opt-in, B200_OPT_PACKED_MATH bit 1). Per power offset the quantiser is a step function of the 31
 // non-sign bits of the power with at most one step per 1/8 octave, except for a band of a few ulps around each step
