@@ -148,3 +148,20 @@ def test_clients_edges_and_mode_switch(gpu_required):
     changes = {5: [(0, LSB), (5, AM)], 9: [(0, AM), (1, FM), (5, USB)], 12: [(0, USB)]}
     stats = run_case(cfg, clients, nframes=16, mode_changes=changes)
     assert stats["pcm_max"] <= 2, stats
+
+
+def test_wbfm_width_clients(gpu_required):
+    """WBFM-width clients (default window +-96 kHz at 192 kHz audio, src/spectrumserver.cpp:137-140): a 10 488-point
+    audio FFT (2^3 * 3 * 19 * 23: generic prime radices), slices of ~10 000 bins and a 512-sample DC blocker - the sizes
+    at which the engine falls back from the warp-per-client demodulation and the pipelined tails to its general
+    kernels. Same bars as the narrow-band cases."""
+    cfg = SpectrumConfig(sps=2_400_000, fft_size=1 << 17, audio_sps=192000)
+    n = cfg.audio_fft_size
+    assert n == 10488
+    R = cfg.fft_result_size
+    half = int(96000 / (cfg.sps / cfg.fft_size))  # +-96 kHz in bins
+    mids = [R // 4 + 0.25, R // 2 + 1000.5, 3 * R // 4 + 7.0]
+    clients = [ClientSpec(int(m) - half, m, int(m) + half, FM) for m in mids]
+    clients.append(ClientSpec(int(mids[0]) - half // 2, mids[0] + 3.0, int(mids[0]) + half // 2, AM))
+    stats = run_case(cfg, clients, nframes=6)
+    assert stats["pcm_max"] <= 2 and stats["fm_off_frac"] <= 0.01, stats
