@@ -1378,16 +1378,15 @@ int b200_engine_create(b200_engine **out, size_t size, int nthreads, int downsam
     return 0;
 }
 
+static void free_client_buffers(b200_engine *e);
 void b200_engine_destroy(b200_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    void *dev[] = {e->d_redo, e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax,
-                   e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop, e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH,
-                   e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM, e->d_done, e->d_qtab, e->d_ring, e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev,
-                   e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last, e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum,
-                   e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre, e->ca.valid_a,
-                   e->ca.pwr, e->ca.pcm, e->ca.valid};
+    free_client_buffers(e);
+    void *dev[] = {e->d_ssync, e->d_winT, e->d_items, e->d_nitems, e->d_prof, e->d_window, e->d_Y, e->d_Z, e->d_spec_raw, e->d_quant, e->d_ptop,
+                   e->d_pscratch, e->d_flags, e->d_flag_err, e->d_twA1, e->d_twA2, e->d_TL, e->d_TH, e->d_TLr, e->d_THr, e->d_pre, e->d_TLM, e->d_THM,
+                   e->d_done, e->d_qtab, e->d_ring};
     for (void *p : dev)
         if (p) cudaFree(p);
     if (e->h_out) cudaFreeHost(e->h_out);
@@ -1927,7 +1926,32 @@ int b200_ipc_close(b200_engine *e, void *dev_ptr) {
 // ------------------------------------------------------------------------------------------------
 // signal slot group
 // ------------------------------------------------------------------------------------------------
+// device / host buffers of the client table (b200_clients_create); safe on a partially created table
+static void free_client_buffers(b200_engine *e) {
+    void *dev[] = {e->d_redo, e->t2.dcx, e->t2.dcm, e->t2.sum, e->t2.gain, e->t2.since, e->t2.blk, e->t2.ring, e->t2.suf, e->t2.cmax,
+                   e->d_order, (void *)e->ca.Wn, e->ca.slots, e->ca.real_prev, e->ca.real_hi, e->ca.hi_diverged, e->ca.bb_hi, e->ca.bb_last,
+                   e->ca.dc_x, e->ca.dc_m, e->ca.dc_sum, e->ca.agc_ring, e->ca.agc_cmax, e->ca.agc_gain, e->ca.agc_t0, e->ca.audio_pre,
+                   e->ca.valid_a, e->ca.pwr, e->ca.pcm, e->ca.valid};
+    for (void *p : dev)
+        if (p) cudaFree(p);
+    if (e->h_tail_err) cudaFreeHost(e->h_tail_err);
+    e->h_tail_err = nullptr;
+    e->d_redo = nullptr;
+    e->d_order = nullptr;
+    e->t2 = Tail2State{};
+    e->ca = ClientArrays{};
+    e->have_clients = false;
+    e->use_tail2 = false;
+}
+
+static int clients_create_impl(b200_engine *e, int max_clients, int audio_fft_size, int audio_max_sps);
 int b200_clients_create(b200_engine *e, int max_clients, int audio_fft_size, int audio_max_sps) {
+    const int rc = clients_create_impl(e, max_clients, audio_fft_size, audio_max_sps);
+    // a failure half way (out of memory, unsupported size) leaves nothing behind: the call can be repeated with other sizes
+    if (rc && e && !e->have_clients) free_client_buffers(e);
+    return rc;
+}
+static int clients_create_impl(b200_engine *e, int max_clients, int audio_fft_size, int audio_max_sps) {
     if (!e) return fail(B200_EINVAL, "null engine");
     if (!e->planned) return fail(B200_ESTATE, "clients_create before plan");
     if (e->have_clients) return fail(B200_ESTATE, "clients already created");

@@ -165,3 +165,35 @@ def test_wbfm_width_clients(gpu_required):
     clients.append(ClientSpec(int(mids[0]) - half // 2, mids[0] + 3.0, int(mids[0]) + half // 2, AM))
     stats = run_case(cfg, clients, nframes=6)
     assert stats["pcm_max"] <= 2 and stats["fm_off_frac"] <= 0.01, stats
+
+
+def test_clients_create_can_be_repeated_after_a_failure(gpu_required):
+    """A client table that fails half way (here: an audio FFT too long for the demodulation kernels, found after the
+    state arrays have been allocated) leaves nothing behind: the call can be repeated with a supported size and the
+    clients then behave as in any other test."""
+    from phantomsdr_b200.backend import B200Error
+
+    cfg = cfg_for_n(1 << 17, 360)
+    eng = make_engine(cfg)
+    with pytest.raises(B200Error):
+        eng.clients_create(8, 16384, cfg.audio_sps)   # rejected before anything is allocated (additional size < n)
+    eng.close()
+
+    # the failure that happens AFTER allocation needs additional >= n: a fresh engine planned with a large tail
+    from phantomsdr_b200.backend import B200FFT
+    e2 = B200FFT(cfg.fft_size, 1, cfg.downsample_levels, cfg.brightness_offset, 0)
+    e2.set_output_additional_size(16384)
+    e2.plan_c2c()
+    with pytest.raises(B200Error, match="too large"):
+        e2.clients_create(8, 16384, 192000)   # (192 kHz audio: the AGC look-ahead check passes, the size check does not)
+    e2.clients_create(8, 360, cfg.audio_sps)        # no "clients already created", no leak of the first attempt
+    e2.client_open(0, 1000, 1001.0, 1090, USB)
+    ring = [e2.malloc(cfg.hop_floats) for _ in range(2)]
+    src = SignalSource(cfg, seed=3)
+    ring[0][:] = hop_as_floats(src.next_hop())
+    ring[1][:] = hop_as_floats(src.next_hop())
+    e2.load_complex_input(ring[0], ring[1])
+    e2.execute()
+    pcm, pwr, valid = e2.clients_execute(0)
+    assert valid[0] == 1 and not valid[1:].any()
+    e2.close()
