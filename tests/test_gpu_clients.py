@@ -6,8 +6,8 @@ comparison isolates the client chain:
   * slice offsets / placement / parity flip / overlap-add / demod: audio before DC removal within
     1e-5 * max|y| per frame (north_star tolerance; FM compared as a wrapped angle);
   * DC blocker + AGC + int16: BIT-EXACT when the oracle tails are fed the engine's own pre-DC audio
-    (strictly sequential float recurrences restated op-for-op), and within 1 LSB (rare 2) against
-    the full oracle chain;
+    (strictly sequential float recurrences restated op-for-op), and within 1 LSB against the full
+    oracle chain (measured: 1 LSB on fewer than 0.1 % of the samples);
   * pwr within 1e-5 relative.
 """
 import numpy as np
@@ -122,8 +122,9 @@ def test_clients_all_modes(gpu_required, n_target, fft_size, is_real):
     tones = [src.display_bin(t) for t in src.tones]
     clients = make_clients(cfg, 24, modes=(USB, LSB, AM, FM), tones=tones, on_tone_fraction=0.7)
     stats = run_case(cfg, clients, nframes=18)
-    assert stats["pcm_max"] <= 2 and stats["pcm_diff_frac"] <= 0.02, stats
-    assert stats["fm_off_frac"] <= 0.01, stats
+    # measured on B200: at most 1 LSB, on fewer than 0.1 % of the samples; no FM sample off by more than 2 LSB
+    assert stats["pcm_max"] <= 1 and stats["pcm_diff_frac"] <= 0.005, stats
+    assert stats["fm_off_frac"] <= 0.002, stats
 
 
 def test_clients_edges_and_mode_switch(gpu_required):
@@ -147,7 +148,7 @@ def test_clients_edges_and_mode_switch(gpu_required):
     ]
     changes = {5: [(0, LSB), (5, AM)], 9: [(0, AM), (1, FM), (5, USB)], 12: [(0, USB)]}
     stats = run_case(cfg, clients, nframes=16, mode_changes=changes)
-    assert stats["pcm_max"] <= 2, stats
+    assert stats["pcm_max"] <= 1 and stats["fm_off_frac"] <= 0.002, stats   # (measured: 0 and 0)
 
 
 def test_wbfm_width_clients(gpu_required):
@@ -164,7 +165,7 @@ def test_wbfm_width_clients(gpu_required):
     clients = [ClientSpec(int(m) - half, m, int(m) + half, FM) for m in mids]
     clients.append(ClientSpec(int(mids[0]) - half // 2, mids[0] + 3.0, int(mids[0]) + half // 2, AM))
     stats = run_case(cfg, clients, nframes=6)
-    assert stats["pcm_max"] <= 2 and stats["fm_off_frac"] <= 0.01, stats
+    assert stats["pcm_max"] <= 1 and stats["fm_off_frac"] <= 0.002, stats   # (measured: 0 and 0)
 
 
 def test_clients_create_can_be_repeated_after_a_failure(gpu_required):
