@@ -74,12 +74,13 @@ def parse_args():
     ap.add_argument("--e2e-raw", default="", choices=["", "s16", "u8"],
                     help="also time the e2e path with raw ADC samples handed to b200_load_raw_input's block form (SURVEY 8f N1: "
                          "sample conversion fused into FFT pass 1, 2x / 4x fewer H2D bytes); reported as e2e_raw, never as e2e")
-    ap.add_argument("--mgpu-mode", default="scatter-dma", choices=["spectrum", "scatter", "scatter-dma"],
+    ap.add_argument("--mgpu-mode", default="scatter-dma", choices=["spectrum", "scatter", "scatter-dma", "scatter-pull"],
                     help="N>1 exchange step. spectrum: NCCL broadcast of every spectrum batch (north_star's wording). scatter: "
                          "clients partitioned in (l, r) order and FFT pass 2 on the ingest rank stores each rank's sub-band "
                          "straight into that rank's memory over NVLink (peer stores fused into the kernel, flags instead of a "
                          "collective). scatter-dma (default, fastest measured: 194 vs 130 vs 129 GS/s at N=8): same partition "
-                         "and flags, the sub-bands pushed by the copy engines so the ingest rank's SMs never wait on NVLink")
+                         "and flags, the sub-bands pushed by the copy engines so the ingest rank's SMs never wait on NVLink. "
+                         "scatter-pull: every client rank's own copy engine fetches its sub-band from the ingest rank's bank")
     args = ap.parse_args()
     explicit = {a.split("=")[0] for a in sys.argv[1:] if a.startswith("--")}
     if args.config == "cfg1":
@@ -373,6 +374,10 @@ def workload_config(cfg, args, world):
                        f"contiguous blocks; copy engines push each rank's sub-band of every batch into that rank's HBM over "
                        f"NVLink (CUDA IPC, stream-ordered flags, no SM time, no collective); "
                        f"{args.clients} clients demodulated per rank" if (args.mgpu_mode == "scatter-dma" and not cfg.is_real) else
+                       f"rank 0 ingests + forward FFT; clients of the whole job sorted by (l, r) and split into {world} "
+                       f"contiguous blocks; every client rank's copy engine pulls its sub-band of every batch from the ingest "
+                       f"rank's HBM over NVLink (CUDA IPC, stream-ordered flags, no SM time, no collective); "
+                       f"{args.clients} clients demodulated per rank" if (args.mgpu_mode == "scatter-pull" and not cfg.is_real) else
                        f"rank 0 ingests + forward FFT; NCCL broadcast of each spectrum batch over NVLink on a "
                        f"communication stream (overlaps the next batch's FFT); "
                        f"{args.clients} clients demodulated per rank ({world} ranks)"),
@@ -398,7 +403,7 @@ def run_b200(args):
     if world > 1 and not args.no_mgpu_extras and not cfg.is_real:
         # the other exchange modes (weak scaling, same client load) and a strong-scaling leg (1024 clients in total)
         extras = {}
-        for mode in ("spectrum", "scatter", "scatter-dma"):
+        for mode in ("spectrum", "scatter", "scatter-dma", "scatter-pull"):
             if mode == args.mgpu_mode:
                 continue
             a2 = copy.copy(args)
@@ -433,7 +438,7 @@ def run_b200(args):
         if rank == 0:
             bad = [f"rank {i}: {v}" for i, v in enumerate(flags) if v != "ok"]
             line["mgpu"]["exchange_parity"] = ("PCM of every rank bit-identical to a local recomputation for NCCL broadcast, "
-                                               "fused peer stores and copy-engine scatter (c2c 2^20 and r2c 2^21)") if not bad else bad
+                                               "fused peer stores, copy-engine push and copy-engine pull (c2c 2^20 and r2c 2^21)") if not bad else bad
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -462,8 +467,9 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
         eng.set_option(OPT_PCM16, 1)
     eng.set_waterfall_cadence(wf_skip)
     eng.clients_create(args.clients, n, cfg.audio_sps)
-    scatter = world > 1 and args.mgpu_mode in ("scatter", "scatter-dma") and not cfg.is_real
+    scatter = world > 1 and args.mgpu_mode in ("scatter", "scatter-dma", "scatter-pull") and not cfg.is_real
     dma = args.mgpu_mode == "scatter-dma"
+    pull = args.mgpu_mode == "scatter-pull"
     if scatter:
         # the (l, r)-sorted client list of the WHOLE job, split into contiguous equal blocks
         from phantomsdr_b200.parallel import partition_clients
@@ -490,6 +496,7 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
 
     # ---- scatter mode: IPC-mapped peer banks + flags ----
     peer_ready, my_ready, r0_consumed, my_consumed = [], None, [], None
+    remote_spec, my_band = None, None
     ipc_opened = []
     if scatter:
         def sub_band(block):
@@ -516,16 +523,19 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
         if rank == 0:
             ptrs = []
             for g in range(1, world):
-                sp = eng.ipc_open(table[g]["spec"])
                 fl = eng.ipc_open(table[g]["flags"])
-                ipc_opened += [sp, fl]
-                ptrs.append(sp + eng.spectrum_offset)
-                peer_ready.append(fl)                                       # flag 0 of rank g: "bank k has landed"
+                ipc_opened.append(fl)
+                if not pull:
+                    sp = eng.ipc_open(table[g]["spec"])
+                    ipc_opened.append(sp)
+                    ptrs.append(sp + eng.spectrum_offset)
+                peer_ready.append(fl)                                       # flag 0 of rank g: "bank k has landed" / "is ready"
                 r0_consumed.append(flags + 8 * g)                           # flag g of rank 0: "rank g is done with bank k"
-            eng.set_peer_spectra(ptrs)
-            for g in range(1, world):
-                (a0, b0), (a1, b1) = sub_band([everyone[i] for i in parts[g]])
-                eng.set_peer_ranges(g - 1, a0, b0, a1, b1)
+            if not pull:
+                eng.set_peer_spectra(ptrs)
+                for g in range(1, world):
+                    (a0, b0), (a1, b1) = sub_band([everyone[i] for i in parts[g]])
+                    eng.set_peer_ranges(g - 1, a0, b0, a1, b1)
             if dma:
                 from phantomsdr_b200.backend import OPT_PEER_STORES
                 eng.set_option(OPT_PEER_STORES, 0)
@@ -534,6 +544,11 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
             f0 = eng.ipc_open(table[0]["flags"])
             ipc_opened.append(f0)
             my_consumed = f0 + 8 * rank
+            if pull:
+                s0 = eng.ipc_open(table[0]["spec"])
+                ipc_opened.append(s0)
+                remote_spec = s0 + eng.spectrum_offset
+                my_band = sub_band([everyone[i] for i in parts[rank]])
         dist.barrier()
 
     state = {"frame_num": 0, "batch_no": 0}
@@ -560,6 +575,11 @@ def run_leg(args, torch, dist, world, rank, local, dev, full=True):
                     eng.enqueue_wait(False, r0_consumed, seq - args.banks)
                 eng.execute_device(hop0, F)  # pass 2 also stores every rank's sub-band into that rank's bank
                 eng.enqueue_signal(False, peer_ready, seq)
+                eng.clients_execute_device(frame_num, F)
+            elif pull:
+                eng.enqueue_wait(True, [my_ready], seq)
+                eng.pull_spectrum(remote_spec, F, my_band[0][0], my_band[0][1], my_band[1][0], my_band[1][1])
+                eng.enqueue_signal(True, [my_consumed], seq)   # pulled: the ingest rank may reuse its bank
                 eng.clients_execute_device(frame_num, F)
             else:
                 eng.enqueue_wait(True, [my_ready], seq)

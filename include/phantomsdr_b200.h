@@ -198,6 +198,13 @@ size_t b200_device_spectrum_offset(b200_engine *e);
  * selected bank (`nframes` frames) into that peer's bank on the engine's copy stream (selector 2 of the flag
  * calls). Use with b200_set_option(B200_OPT_PEER_STORES, 0). */
 int b200_push_peers(b200_engine *e, int nframes);
+/* Pull form of the scatter, called on a CLIENT rank: copy this rank's sub-band (two half-open bin ranges, as
+ * b200_set_peer_ranges) of the selected bank from the ingest rank's spectrum (an IPC mapping of its
+ * b200_device_spectrum_base() + b200_device_spectrum_offset()) into the same bank here, on the client stream - behind
+ * the b200_enqueue_wait for the ingest rank's "bank ready" flag and in front of b200_clients_execute_device. The copy
+ * is done by THIS GPU's copy engine, so the pulls of seven client ranks run on seven engines instead of the ingest
+ * rank's own. */
+int b200_pull_spectrum(b200_engine *e, const void *remote_spectrum, int nframes, uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1);
 void *b200_flag_buffer(b200_engine *e);
 int b200_enqueue_signal(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t value);
 int b200_enqueue_wait(b200_engine *e, int client_stream, void *const *flag_ptrs, int n, uint64_t min_value, int timeout_ms);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200_device_spectrum_base": (_vp, [_vp]),
     "b200_device_spectrum_offset": (_sz, [_vp]),
     "b200_push_peers": (_i, [_vp, _i]),
+    "b200_pull_spectrum": (_i, [_vp, _vp, _i, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "b200_flag_buffer": (_vp, [_vp]),
     "b200_enqueue_signal": (_i, [_vp, _i, _pp, _i, _u64]),
     "b200_enqueue_wait": (_i, [_vp, _i, _pp, _i, _u64, _i]),

@@ -234,6 +234,9 @@ class B200FFT:
     def push_peers(self, nframes: int) -> None:
         check(self.L.b200_push_peers(self.h, nframes))
 
+    def pull_spectrum(self, remote_spectrum: int, nframes: int, lo0: int, hi0: int, lo1: int = 0, hi1: int = 0) -> None:
+        check(self.L.b200_pull_spectrum(self.h, remote_spectrum, nframes, lo0, hi0, lo1, hi1))
+
     @property
     def spectrum_base(self) -> int:
         return self.L.b200_device_spectrum_base(self.h)

@@ -1856,6 +1856,25 @@ int b200_push_peers(b200_engine *e, int nframes) {
     e->push_pending[e->cur_bank] = true;
     return 0;
 }
+int b200_pull_spectrum(b200_engine *e, const void *remote_spectrum, int nframes, uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1) {
+    if (!e || !remote_spectrum) return fail(B200_EINVAL, "null argument");
+    if (nframes < 1 || nframes > e->batch) return fail(B200_EINVAL, "nframes %d outside 1..%d", nframes, e->batch);
+    if (e->spec_bound) return fail(B200_ESTATE, "spectrum is bound to an external buffer");
+    CU(cudaSetDevice(e->device));
+    // the ingest rank's bank -> the same bank here, by THIS GPU's copy engine, behind whatever the client stream already
+    // holds (the wait for the ingest rank's "bank ready" flag) and in front of the demodulation that follows
+    const size_t bank_off = (size_t)e->cur_bank * e->batch * e->spec_stride;
+    const float2 *src = static_cast<const float2 *>(remote_spectrum) + bank_off;
+    float2 *dst = e->d_spec + bank_off;
+    const size_t pitch = e->spec_stride * sizeof(float2);
+    const uint32_t lo[2] = {lo0, lo1}, hi[2] = {hi0, hi1};
+    for (int j = 0; j < 2; j++) {
+        const size_t a = lo[j], b = std::min<size_t>(hi[j], e->spec_stride);
+        if (b <= a) continue;
+        CU(cudaMemcpy2DAsync(dst + a, pitch, src + a, pitch, (b - a) * sizeof(float2), nframes, cudaMemcpyDeviceToDevice, e->client_stream()));
+    }
+    return 0;
+}
 static int flag_list(b200_engine *e, void *const *flag_ptrs, int n, FlagList *fl) {
     if (!e || !flag_ptrs) return fail(B200_EINVAL, "null argument");
     if (n < 1 || n > kMaxPeers) return fail(B200_EINVAL, "1..%d flags per call", kMaxPeers);

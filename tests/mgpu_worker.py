@@ -76,32 +76,40 @@ def exchange_case(cfg, local, dev, rank, world):
             e.select_bank(b)
             banks.append(torch.as_tensor(e.device_spectrum(F), device=dev))
         peer_ready, r0_consumed, my_ready, my_consumed = [], [], None, None
-        if mode in ("scatter", "scatter-dma"):
+        remote, my_range = None, None
+
+        def block_ranges(g):  # the two half-open bin ranges (below / above the wrap point of the display axis) rank g needs
+            blk = [everyone[i] for i in parts[g]]
+            iv = sorted((cfg.slice_offset(c.l), cfg.slice_offset(c.l) + c.r - c.l) for c in blk)
+            half = cfg.fft_result_size // 2
+            low = [x for x in iv if x[0] < half]
+            high = [x for x in iv if x[0] >= half]
+            return [(min(a for a, _ in part), max(b for _, b in part)) if part else (0, 0) for part in (low, high)]
+
+        if mode in ("scatter", "scatter-dma", "scatter-pull"):
             flags = e.flag_buffer
             table = [None] * world
             dist.all_gather_object(table, {"spec": e.ipc_export(e.spectrum_base), "flags": e.ipc_export(flags)})
             if rank == 0:
                 ptrs = []
                 for g in range(1, world):
-                    ptrs.append(e.ipc_open(table[g]["spec"]) + e.spectrum_offset)
+                    if mode != "scatter-pull":
+                        ptrs.append(e.ipc_open(table[g]["spec"]) + e.spectrum_offset)
                     peer_ready.append(e.ipc_open(table[g]["flags"]))
                     r0_consumed.append(flags + 8 * g)
-                e.set_peer_spectra(ptrs)
-                for g in range(1, world):
-                    blk = [everyone[i] for i in parts[g]]
-                    lo = min(cfg.slice_offset(c.l) for c in blk)
-                    iv = sorted((cfg.slice_offset(c.l), cfg.slice_offset(c.l) + c.r - c.l) for c in blk)
-                    # two ranges: below / above the wrap point of the display axis
-                    half = cfg.fft_result_size // 2
-                    low = [x for x in iv if x[0] < half]
-                    high = [x for x in iv if x[0] >= half]
-                    r = [(min(a for a, _ in part), max(b for _, b in part)) if part else (0, 0) for part in (low, high)]
-                    e.set_peer_ranges(g - 1, r[0][0], r[0][1], r[1][0], r[1][1])
+                if mode != "scatter-pull":
+                    e.set_peer_spectra(ptrs)
+                    for g in range(1, world):
+                        r = block_ranges(g)
+                        e.set_peer_ranges(g - 1, r[0][0], r[0][1], r[1][0], r[1][1])
                 if mode == "scatter-dma":
                     e.set_option(OPT_PEER_STORES, 0)
             else:
                 my_ready = flags
                 my_consumed = e.ipc_open(table[0]["flags"]) + 8 * rank
+                if mode == "scatter-pull":  # this rank's copy engine fetches its sub-band from the ingest rank's bank
+                    remote = e.ipc_open(table[0]["spec"]) + e.spectrum_offset
+                    my_range = block_ranges(rank)
             dist.barrier()
         ex = SpectrumExchange(world, rank)
         out = []
@@ -133,8 +141,11 @@ def exchange_case(cfg, local, dev, rank, world):
                     e.enqueue_signal(False, peer_ready, seq)
                 else:
                     e.enqueue_wait(True, [my_ready], seq)
+                    if mode == "scatter-pull":
+                        e.pull_spectrum(remote, F, my_range[0][0], my_range[0][1], my_range[1][0], my_range[1][1])
+                        e.enqueue_signal(True, [my_consumed], seq)  # the ingest rank may reuse its bank
             e.clients_execute_device(k * F, F)
-            if mode != "local" and mode != "broadcast" and rank != 0:
+            if mode in ("scatter", "scatter-dma") and rank != 0:
                 e.enqueue_signal(True, [my_consumed], seq)
             for f in range(F):
                 pcm, pwr, valid = e.clients_fetch(f)
@@ -144,13 +155,13 @@ def exchange_case(cfg, local, dev, rank, world):
         e.sync()
         if e.flag_error != 0:
             problems.append(f"rank {rank} mode {mode}: a peer flag wait timed out")
-        if mode in ("scatter", "scatter-dma"):
+        if mode in ("scatter", "scatter-dma", "scatter-pull"):
             dist.barrier()
         e.close()
         return out
 
     ref = run("local")
-    for mode in ("broadcast", "scatter", "scatter-dma"):
+    for mode in ("broadcast", "scatter", "scatter-dma", "scatter-pull"):
         got = run(mode)
         for f, (a, b) in enumerate(zip(ref, got)):
             if not np.array_equal(a, b):
