@@ -259,6 +259,7 @@ struct b200_engine {
     int opt_demod_chunk = -1;           // frames per warp task of the frame-chunked demodulation (0 = sequential kernel only,
                                         // -1 = chosen per launch: see demod_chunk_for)
     int flag_waits = 0;                 // b200_enqueue_wait calls since stream_check last read the flag error word
+    size_t tail2_dyn = 0;               // dynamic shared memory of a tail CTA (tail2_dynamic_smem)
     int opt_tail_smem_kb = 224;         // shared memory a tail CTA asks for: with its 3 KB of static memory exactly the SM's 227 KB,
                                         // so that no other CTA (not even a pyramid CTA with 1 KB) shares its schedulers
     int opt_r2c_split = 1;              // r2c: Hermitian split as its own streaming kernel + the c2c pyramid kernel (0: one kernel)
@@ -1199,17 +1200,33 @@ template <int KB> int launch_tail_kb(b200_engine *e, const ClientArrays &ca, con
     CU(cudaGetLastError());
     return 0;
 }
+// Dynamic shared memory of a tail CTA: what the pipeline needs, raised to the requested size (default: the whole SM) but
+// never beyond what the device grants a block once the kernel's static shared memory is taken off.
+static size_t tail2_dynamic_smem(const b200_engine *e) {
+    size_t want = std::max(tail2_smem(e->ca.D), (size_t)e->opt_tail_smem_kb * 1024);
+    cudaFuncAttributes fa{};
+    int optin = 0;
+    if (cudaFuncGetAttributes(&fa, client_tail2_kernel<1>) == cudaSuccess &&
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device) == cudaSuccess && optin > 0) {
+        const size_t room = (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+        want = std::min(want, room);
+    }
+    return want;
+}
+
 int launch_tail2(b200_engine *e, const ClientArrays &ca, const ClientLaunch &cl) {
     // One group of 32 clients per CTA, and the CTA asks for ALL the shared memory of its SM although it needs 204 KB:
     // every stage of the pipeline is a single warp on the critical path, and warps of other CTAs competing for the SM's
     // issue slots slow the whole chain. Measured at 1024 clients beside the forward kernels (cycles per frame of a
     // stage-profiled CTA): alone 16.4 K; beside the forward kernels 22.3 K at 204 KB (pyramid CTAs move in), 19.3 K at
     // 224 KB. Two groups per SM (two CTAs, or one CTA of twice the warps) cost every stage 40 %.
-    const size_t smem = std::max(tail2_smem(e->ca.D), (size_t)e->opt_tail_smem_kb * 1024);
     if (cl.nactive == 0) {  // preparation call from clients_create
-        CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        e->tail2_dyn = tail2_dynamic_smem(e);
+        if (e->tail2_dyn < tail2_smem(e->ca.D)) return fail(B200_ENOTSUP, "tail pipeline needs %zu bytes of shared memory", tail2_smem(e->ca.D));
+        CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tail2_dyn));
         return 0;
     }
+    const size_t smem = e->tail2_dyn;
     const int groups = (e->ca.max_clients + 31) / 32;
     client_tail2_kernel<1><<<groups, kT2Threads, smem, e->tail_stream()>>>(ca, cl, e->t2, groups);
     e->launches++;
@@ -1581,9 +1598,10 @@ int b200_debug_option(b200_engine *e, int option, int value) {
     case B200_OPT_TAIL_SMEM_KB:
         if (value < 0 || value > 224) return fail(B200_EINVAL, "tail shared memory must be 0..224 KB");
         e->opt_tail_smem_kb = value;
-        if (e->have_clients && e->use_tail2)
-            CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)std::max(tail2_smem(e->ca.D), (size_t)value * 1024)));
+        if (e->have_clients && e->use_tail2) {
+            e->tail2_dyn = tail2_dynamic_smem(e);
+            CU(cudaFuncSetAttribute(client_tail2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tail2_dyn));
+        }
         return 0;
     case B200_OPT_FWD_SMS:
         if (value < 0 || value > 1024) return fail(B200_EINVAL, "forward SM count must be 0 (all) .. 1024");
