@@ -586,11 +586,9 @@ template <int MODE, int PER, bool PK, bool CG, bool TB = false, typename Sync = 
 __device__ __forceinline__ void pyramid_block(const PyrParams &p, const int frame, const unsigned blk, const int tid,
                                               float *warp_sum_s, Sync sync) {
     static_assert(PER == 4 || PER == 16, "PER must be 4 or 16");
-    constexpr int LP = (PER == 16) ? 4 : 2;  // levels reduced in registers
     const unsigned R = 1u << p.log2R;  // bins and pyramid offsets fit 32 bits (R <= 2^23)
     const int B = (MODE == PYR_SCRATCH) ? p.base_level : 0;
     const unsigned d0 = (blk * 256u + tid) * PER;  // index at level B
-    int8_t *quant = p.quant + (size_t)frame * p.pyr_stride;
 
     float pw[PER];
     if constexpr (MODE == PYR_SPEC) {
