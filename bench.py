@@ -9,15 +9,24 @@ A step = one pass of the hot path over one ring of synthetic input: `ring` hops 
 HBM (ring x 4 MiB > L2, so no step re-reads its input from cache) -> `ring` 50 %-overlapped frames,
 each: fused window+forward FFT -> int8 waterfall pyramid -> gather/IFFT/demod/DC/AGC/int16 for every
 client. `value` = IQ samples all ranks processed / device time (CUDA events, max over ranks).
-`e2e` = the same frames through the reference-facing C-ABI calls with HOST buffers
-(b200_load_complex_input -> b200_execute -> b200_clients_execute), host<->device copies inside.
+`e2e` = the same frames through the reference-facing C-ABI calls with HOST buffers in their block form
+(b200_submit_block / b200_wait_block = load_complex_input -> execute -> signal_loop for 64 frames per call, up to
+four blocks in flight), every host<->device copy inside the timed region. Other keys: `roofline` (forward group
+timed alone; `traffic` from profiles/r2_traffic*.json, which names its build), `cpu_baseline` (oracle port + MKL on
+the host cores, with the forward / clients split and the one-thread-FFT variant), `breakdown` (stage-isolated
+timings and the bare cuFFT transform), `clocks`, `gpu_launches`.
+
+Options: --config cfg1|cfg2|cfg3 (BASELINE configs), --waterfall-skip 0 (the reference's send cadence), --pcm16,
+--e2e-raw s16|u8 (raw ADC halves, extra key `e2e_raw`), --mgpu-mode spectrum|scatter|scatter-dma|scatter-pull,
+--impl cufft (library yardstick), --impl reference (CPU arm).
 
 N > 1 (torchrun): rank 0 ingests and computes each spectrum batch, one exchange step over NVLink delivers it
 to every rank, every rank demodulates its own 1024 clients of the whole stream (weak scaling: per-GPU client
 load fixed). `value` = ingest rate x client shards (= ingest x clients_total / 1024): the stream rate the job
 sustains per 1024-client shard, summed over the N shards; `ingest_msps` is the rate of the ONE ingested
-stream. The same run also times the other exchange modes and a strong-scaling leg (1024 clients in total) and
-reports them under "mgpu". --impl reference uses the same definition on the same client total.
+stream. The same run also times the other exchange modes and a strong-scaling leg (1024 clients in total), runs
+the exchange parity check of tests/mgpu_worker.py in its own process group, and reports all of it under "mgpu".
+--impl reference uses the same definition on the same client total.
 
 --impl reference : the reference's CPU path (oracle port; FFT by MKL through torch.fft as the
 FFTW substitute) on the host cores, same config/metric, bounded sample per step.
